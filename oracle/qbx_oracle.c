@@ -1,0 +1,567 @@
+/*
+ * qbx_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A plain-C restatement of the algorithm Quiqbox.jl v0.6.3 uses on the ERI + J/K hot
+ * path.  It exists only so that tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs can check (or time) the CUDA product path against
+ * an independent implementation of the reference's arithmetic.  Nothing under
+ * quiqbox.jl_b200/ may import, link or call this file.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file against every
+ * known-answer vector the reference's own tests hold for the path:
+ *   test/unit-tests/Integration/BoysFunction-test.jl:6-32   (15 Boys points + 2 sequence)
+ *   test/unit-tests/Integration/Coulomb-test.jl:32-45,56-81 (primitive 1- and 2-body)
+ *   test/unit-tests/Integration/Coulomb-test.jl:139-154     (LiH V2, 8-fold symmetry)
+ *   test/unit-tests/HartreeFock-test.jl:92,152,221-258,296  (SCF energies)
+ *
+ * Every function cites the reference file:line it follows (paths relative to the
+ * reference root).  The reference is pure Julia and cannot run in the build container,
+ * so this restatement -- not the Julia -- is what executes.
+ *
+ * Third-party arithmetic: the reference's Boys function calls SpecialFunctions.jl
+ * (compat >= 2.5.1, Project.toml:30; no Manifest so no exact pin) for gamma_inc, gamma,
+ * loggamma and erf (BoysFunction.jl:1-2).  That package is not in the reference tree;
+ * here the regularised lower incomplete gamma P(a,x) is computed with the textbook
+ * series / Lentz continued-fraction pair (Numerical Recipes 6.2; DiDonato & Morris 1986
+ * use the same two expansions in this regime) in long double, and erf/lgamma/tgamma come
+ * from libm.  The boundary is pinned by BoysFunction-test.jl.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAXL 96           /* max total angular momentum on one quartet            */
+#define ORC_PI 3.14159265358979323846264338327950288L
+
+/* ------------------------------------------------------------------------------------ */
+/* Boys function  (src/Integration/Engines/BoysFunction.jl)                             */
+/* ------------------------------------------------------------------------------------ */
+
+/* regularised lower incomplete gamma P(a,x); stands in for SpecialFunctions.gamma_inc
+ * (BoysFunction.jl:11) */
+static long double orc_gamma_p(long double a, long double x)
+{
+    if (x <= 0.0L) return 0.0L;
+    long double lg = lgammal(a);
+    if (x < a + 1.0L) {                       /* power series */
+        long double ap = a, del = 1.0L / a, sum = del;
+        for (int n = 0; n < 100000; ++n) {
+            ap += 1.0L; del *= x / ap; sum += del;
+            if (fabsl(del) < fabsl(sum) * 1e-21L) break;
+        }
+        return sum * expl(-x + a * logl(x) - lg);
+    } else {                                  /* continued fraction for Q, modified Lentz */
+        const long double tiny = 1e-4000L;
+        long double b = x + 1.0L - a, c = 1.0L / tiny, d = 1.0L / b, h = d;
+        for (int i = 1; i < 100000; ++i) {
+            long double an = -(long double)i * ((long double)i - a);
+            b += 2.0L;
+            d = an * d + b; if (fabsl(d) < tiny) d = tiny;
+            c = b + an / c; if (fabsl(c) < tiny) c = tiny;
+            d = 1.0L / d;
+            long double del = d * c; h *= del;
+            if (fabsl(del - 1.0L) < 1e-21L) break;
+        }
+        long double q = expl(-x + a * logl(x) - lg) * h;
+        return 1.0L - q;
+    }
+}
+
+/* directComputeBoysFunc, BoysFunction.jl:7-24 */
+static double orc_boys_direct(double x, int n)
+{
+    long double z = (long double)n + 0.5L;
+    long double p = orc_gamma_p(z, (long double)x);
+    if (p == 0.0L) return 0.0;
+    long double res;
+    if (z < 23.0L) {
+        long double part1 = tgammal(z) * p;
+        long double part2 = powl((long double)x, z);
+        res = isinf((double)part2) ? expl(logl(part1) - z * logl((long double)x))
+                                   : part1 / part2;
+    } else {
+        res = expl(lgammal(z) + logl(p) - z * logl((long double)x));
+    }
+    return (double)(res / 2.0L);
+}
+
+/* initializeUpperOrder, BoysFunction.jl:27-31; getAtolDigits(Float64) = 15
+ * (Arithmetic.jl:8-17) */
+static int orc_boys_upper_order(double x, int n)
+{
+    double arg = ((double)n == x) ? (double)n : (double)n / x;
+    int res = (int)ceil(15.0 / fabs(log10(arg)) + (double)n);
+    return res + (res & 1);
+}
+
+/* recursiveGetBoysFuncDn, BoysFunction.jl:33-40 */
+static double orc_boys_down(double x, int m, double val, int n)
+{
+    for (int i = m - 1; i >= n; --i) val = (2.0 * x * val + exp(-x)) / (2.0 * i + 1.0);
+    return val;
+}
+
+/* getAtolVal(Float64) = ceil(3 eps/2, sigdigits=1) = 4e-16  (Arithmetic.jl:42) */
+#define ORC_ATOL 4e-16
+
+/* computeBoysFunc / ComputeBoysOrderN / computeBoysOrder0, BoysFunction.jl:42-64 */
+double orc_boys(double x, int n)
+{
+    if (n == 0) {
+        if (x < ORC_ATOL) return 1.0;
+        double r = sqrt(x);
+        return (double)sqrtl(ORC_PI) * erf(r) / (2.0 * r);
+    }
+    if (x < ORC_ATOL) return 1.0 / (2.0 * n + 1.0);
+    int up = orc_boys_upper_order(x, n);
+    if (up > 6 * n) up = 6 * n;
+    double fup = orc_boys_direct(x, up);
+    return orc_boys_down(x, up, fup, n);
+}
+
+/* computeBoysSequence, BoysFunction.jl:67-77: out[m] = F_m(x), m = 0..n (ascending) */
+void orc_boys_sequence(double x, int n, double *out)
+{
+    out[0] = orc_boys(x, 0);
+    if (n > 0) out[n] = orc_boys(x, n);
+    for (int m = n; m >= 2; --m) out[m - 1] = orc_boys_down(x, m, out[m], m - 1);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Obara-Saika building blocks (GaussianOrbitals.jl:386-454, 529-592)                   */
+/* ------------------------------------------------------------------------------------ */
+
+/* vertTransfer, GaussianOrbitals.jl:386-391 */
+static inline double orc_vert(double p0m1, double p1m1, double p0m2, double p1m2, int iL,
+                              double xML, double xMC, double xpnSum, double factor)
+{
+    double part1 = xML * p0m1 - factor * xMC * p1m1;
+    double part2 = (iL - 1) * (p0m2 - factor * p1m2) * (1.0 / (2.0 * xpnSum));
+    return part1 + part2;
+}
+
+/* verticalFill!, GaussianOrbitals.jl:401-418.  h[0..iSum] holds auxiliary orders
+ * N..N+iSum of the s-type integral on entry and [i,0]^(N), i = 0..iSum, on exit. */
+static void orc_vertical_fill(double *h, int iSum, double xML, double xMC, double xpnSum,
+                              double factor)
+{
+    for (int n = 1; n <= iSum; ++n) {
+        double b0 = h[iSum - n], b1 = h[iSum - n + 1], b2 = 0.0, b3 = 0.0;
+        for (int i = 1; i <= n; ++i) {
+            double here = orc_vert(b0, b1, b2, b3, i, xML, xMC, xpnSum, factor);
+            if (i < n) {
+                double nb2 = b0, nb3 = b1;
+                b1 = h[iSum - n + i + 1];
+                b0 = here; b2 = nb2; b3 = nb3;
+            }
+            h[iSum - n + i] = here;
+        }
+    }
+}
+
+/* verticalPush!, GaussianOrbitals.jl:423-439: holder[0] is the s-type value one order
+ * below data; fills holder[i] = [i,0]^(n) from data[i] = [i,0]^(n+1). */
+static void orc_vertical_push(double *holder, const double *data, int iSum, double xML,
+                              double xMC, double xpnSum, double factor)
+{
+    double b0 = holder[0], b1 = data[0], b2 = 0.0, b3 = 0.0;
+    for (int i = 1; i <= iSum; ++i) {
+        double here = orc_vert(b0, b1, b2, b3, i, xML, xMC, xpnSum, factor);
+        holder[i] = here;
+        if (i < iSum) { b2 = b0; b3 = b1; b0 = here; b1 = data[i]; }
+    }
+}
+
+/* angularShift! + horiTransfer, GaussianOrbitals.jl:394-396, 446-454.
+ * Operates on the last iR+1 entries of h[0..len-1]; returns [len-1-iR, iR]. */
+static double orc_angular_shift(double *h, int len, int iR, double xLR)
+{
+    double *seg = h + (len - 1 - iR);
+    for (int y = 1; y <= iR; ++y)
+        for (int x = 1; x <= iR + 1 - y; ++x) seg[x - 1] = seg[x] + xLR * seg[x - 1];
+    return seg[0];
+}
+
+/* modeTransfer, GaussianOrbitals.jl:529-538 */
+static inline double orc_mode(double iP0oM2, double iP1oM1, double iP0oM1, double iM1oM1,
+                              int i, int o, double xpnR1, double xpnR2, double xLR1,
+                              double xLR2, double xpnSum1, double xpnSum2)
+{
+    double part1 = (i * iM1oM1 + (o - 1) * iP0oM2) / (2.0 * xpnSum2);
+    double part2 = ((xpnR1 * xLR1 + xpnR2 * xLR2) * iP0oM1 + xpnSum1 * iP1oM1) / xpnSum2;
+    return part1 - part2;
+}
+
+#define ORC_MB (ORC_MAXL + 2)
+
+/* orbitalShift! with angularCross! inlined, GaussianOrbitals.jl:543-592.
+ * data[0..angSpace-1] = [i,0|0,0], i = 0..ioSum.  Returns [iL,iR|oL,oR] and
+ * overwrites data. */
+static double orc_orbital_shift(double (*M)[ORC_MB], double *data, int angSpace, int oSum,
+                                int iR, int oR, double xpnR1, double xpnR2, double xLR1,
+                                double xLR2, double xpnSum1, double xpnSum2)
+{
+    for (int c = 0; c < angSpace; ++c) M[0][c] = data[c];
+    for (int o = 1; o <= oSum; ++o) {
+        int n = angSpace - o - 1;
+        double iP1oM1 = M[o - 1][n + 1];
+        double iP0oM1 = M[o - 1][n];
+        double iM1oM1 = n > 0 ? M[o - 1][n - 1] : 0.0;
+        double iP0oM2 = o > 1 ? M[o - 2][n] : 0.0;
+        for (int i = n; i >= 0; --i) {
+            M[o][i] = orc_mode(iP0oM2, iP1oM1, iP0oM1, iM1oM1, i, o, xpnR1, xpnR2, xLR1,
+                               xLR2, xpnSum1, xpnSum2);
+            iP1oM1 = iP0oM1;
+            iP0oM1 = iM1oM1;
+            iM1oM1 = i > 1 ? M[o - 1][i - 2] : 0.0;
+            iP0oM2 = (i > 0 && o > 1) ? M[o - 2][i - 1] : 0.0;
+        }
+    }
+    int ncol = angSpace - oSum;           /* columns i = 0..iSum of electron 1 */
+    double slot[ORC_MB];
+    for (int c = 0; c < ncol; ++c) {
+        for (int o = 0; o <= oSum; ++o) slot[o] = M[o][c];
+        data[c] = orc_angular_shift(slot, oSum + 1, oR, xLR2);
+    }
+    return orc_angular_shift(data, ncol, iR, xLR1);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Primitive integrals.  A primitive is x_A^i y_A^j z_A^k exp(-a r_A^2), unnormalised.   */
+/* ------------------------------------------------------------------------------------ */
+
+/* computePGTOrbTwoBodyRepulsion!, GaussianOrbitals.jl:594-663.
+ * cen: 4x3 (L1,R1,L2,R2), xpn: 4, ang: 4x3. */
+double orc_prim_eri(const double *cen, const double *xpn, const int *ang)
+{
+    const double *cL1 = cen, *cR1 = cen + 3, *cL2 = cen + 6, *cR2 = cen + 9;
+    const int *aL1 = ang, *aR1 = ang + 3, *aL2 = ang + 6, *aR2 = ang + 9;
+    double xpnR1 = xpn[1], xpnSum1 = xpn[0] + xpn[1], xpnPOS1 = xpn[0] * xpnR1 / xpnSum1;
+    double xpnR2 = xpn[3], xpnSum2 = xpn[2] + xpn[3], xpnPOS2 = xpn[2] * xpnR2 / xpnSum2;
+    double cM1[3], cM2[3];
+    /* GaussProductInfo, GaussianOrbitals.jl:24-36: identical primitives keep the centre */
+    int same1 = (xpn[0] == xpn[1]) && !memcmp(cL1, cR1, 3 * sizeof(double)) &&
+                !memcmp(aL1, aR1, 3 * sizeof(int));
+    int same2 = (xpn[2] == xpn[3]) && !memcmp(cL2, cR2, 3 * sizeof(double)) &&
+                !memcmp(aL2, aR2, 3 * sizeof(int));
+    for (int d = 0; d < 3; ++d) {
+        cM1[d] = same1 ? cL1[d] : (xpn[0] * cL1[d] + xpn[1] * cR1[d]) / xpnSum1;
+        cM2[d] = same2 ? cL2[d] : (xpn[2] * cL2[d] + xpn[3] * cR2[d]) / xpnSum2;
+    }
+    int angSum = 0, ioS[3], oS[3];
+    double r2_12 = 0;
+    for (int d = 0; d < 3; ++d) {
+        oS[d] = aL2[d] + aR2[d];
+        ioS[d] = aL1[d] + aR1[d] + oS[d];
+        angSum += ioS[d];
+        double d12 = cM1[d] - cM2[d];
+        r2_12 += d12 * d12;
+    }
+    if (angSum > ORC_MAXL) return NAN;
+    double xpnSumPOS = xpnSum1 * xpnSum2 / (xpnSum1 + xpnSum2);
+    double xpnFactor = xpnSumPOS / xpnSum1;
+    /* computePGTOrbMixedFactorProd, :378-382: product of per-axis exponentials */
+    double pre1 = 1.0, pre2 = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        double d1 = cL1[d] - cR1[d], d2 = cL2[d] - cR2[d];
+        pre1 *= exp(-xpnPOS1 * d1 * d1);
+        pre2 *= exp(-xpnPOS2 * d2 * d2);
+    }
+    pre1 /= xpnSum1; pre2 /= xpnSum2;
+    double factor = 2.0 * (double)powl(ORC_PI, 2.5L) * pre1 * pre2 / sqrt(xpnSum1 + xpnSum2);
+
+    double hori[ORC_MAXL + 1], vert[ORC_MAXL + 1], next[ORC_MAXL + 1];
+    static _Thread_local double mode[ORC_MB][ORC_MB];
+    orc_boys_sequence(xpnSumPOS * r2_12, angSum, hori);
+    memcpy(vert, hori, sizeof(double) * (angSum + 1));
+    int end = angSum;                      /* index of `last(horiBuffer)` */
+    int nUpper = angSum;
+    for (int d = 0; d < 3; ++d) {
+        int ioSum = ioS[d], oSum = oS[d], iR = aR1[d], oR = aR2[d];
+        double xML1 = cM1[d] - cL1[d], xLR1 = cL1[d] - cR1[d], xLR2 = cL2[d] - cR2[d];
+        double xM1M2 = cM1[d] - cM2[d];
+        int nShift = nUpper - ioSum;
+        double *segHere = hori + (end - ioSum);
+        orc_vertical_fill(segHere, ioSum, xML1, xM1M2, xpnSum1, xpnFactor);
+        for (int s = 1; s <= nShift; ++s) {
+            int sMax = s + ioSum;
+            /* vertSegNext = vertBuffer[end-sMax : end-s] */
+            memcpy(next, vert + (end - sMax), sizeof(double) * (ioSum + 1));
+            orc_vertical_push(next, segHere, ioSum, xML1, xM1M2, xpnSum1, xpnFactor);
+            hori[end - s + 1] = orc_orbital_shift(mode, segHere, ioSum + 1, oSum, iR, oR,
+                                                  xpnR1, xpnR2, xLR1, xLR2, xpnSum1, xpnSum2);
+            segHere = hori + (end - sMax);
+            memcpy(segHere, next, sizeof(double) * (ioSum + 1));
+            memcpy(vert + (end - sMax), next, sizeof(double) * (ioSum + 1));
+        }
+        hori[end - nShift] = orc_orbital_shift(mode, segHere, ioSum + 1, oSum, iR, oR, xpnR1,
+                                               xpnR2, xLR1, xLR2, xpnSum1, xpnSum2);
+        memcpy(vert, hori, sizeof(double) * (angSum + 1));
+        nUpper -= ioSum;
+    }
+    return factor * hori[end];
+}
+
+/* computePGTOrbOneBodyRepulsion!, GaussianOrbitals.jl:478-522.
+ * cen: 2x3 (L,R), point: 3. */
+double orc_prim_nuclear(const double *cen, const double *xpn, const int *ang,
+                        const double *point)
+{
+    const double *cL = cen, *cR = cen + 3;
+    const int *aL = ang, *aR = ang + 3;
+    double xpnSum = xpn[0] + xpn[1], xpnPOS = xpn[0] * xpn[1] / xpnSum;
+    int same = (xpn[0] == xpn[1]) && !memcmp(cL, cR, 3 * sizeof(double)) &&
+               !memcmp(aL, aR, 3 * sizeof(int));
+    double cM[3], r2 = 0, pre = 1.0;
+    int angSum = 0, iS[3];
+    for (int d = 0; d < 3; ++d) {
+        cM[d] = same ? cL[d] : (xpn[0] * cL[d] + xpn[1] * cR[d]) / xpnSum;
+        double dmc = cM[d] - point[d], dlr = cL[d] - cR[d];
+        r2 += dmc * dmc;
+        pre *= exp(-xpnPOS * dlr * dlr);
+        iS[d] = aL[d] + aR[d];
+        angSum += iS[d];
+    }
+    if (angSum > ORC_MAXL) return NAN;
+    double factor = 2.0 * (double)ORC_PI * pre / xpnSum;
+    double hori[ORC_MAXL + 1], vert[ORC_MAXL + 1], next[ORC_MAXL + 1];
+    orc_boys_sequence(xpnSum * r2, angSum, hori);
+    memcpy(vert, hori, sizeof(double) * (angSum + 1));
+    int end = angSum, nUpper = angSum;
+    for (int d = 0; d < 3; ++d) {
+        int iSum = iS[d], iR = aR[d];
+        double xML = cM[d] - cL[d], xLR = cL[d] - cR[d], xMC = cM[d] - point[d];
+        int nShift = nUpper - iSum;
+        double *segHere = hori + (end - iSum);
+        orc_vertical_fill(segHere, iSum, xML, xMC, xpnSum, 1.0);
+        for (int s = 1; s <= nShift; ++s) {
+            int sMax = s + iSum;
+            memcpy(next, vert + (end - sMax), sizeof(double) * (iSum + 1));
+            orc_vertical_push(next, segHere, iSum, xML, xMC, xpnSum, 1.0);
+            hori[end - s + 1] = orc_angular_shift(segHere, iSum + 1, iR, xLR);
+            segHere = hori + (end - sMax);
+            memcpy(segHere, next, sizeof(double) * (iSum + 1));
+            memcpy(vert + (end - sMax), next, sizeof(double) * (iSum + 1));
+        }
+        hori[end - nShift] = orc_angular_shift(segHere, iSum + 1, iR, xLR);
+        memcpy(vert, hori, sizeof(double) * (angSum + 1));
+        nUpper -= iSum;
+    }
+    return factor * hori[end];
+}
+
+static double orc_binom(int n, int k)
+{
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
+/* computePGTOrbOverlapAxialFactor, GaussianOrbitals.jl:94-97 (oddFactorial with a
+ * coefficient: Arithmetic.jl:101-107) */
+static double orc_axial_factor(double xpnSum, int degree)
+{
+    double f = 1.0;
+    if (degree > 0) for (int i = 1; i <= 2 * degree - 1; i += 2) f *= i * (1.0 / (2.0 * xpnSum));
+    return (double)sqrtl(ORC_PI) / sqrt(xpnSum) * f;
+}
+
+/* computeGaussProd, Arithmetic.jl:110-120 */
+static double orc_gauss_prod(double dxML, double dxMR, int lL, int lR, int lx)
+{
+    int lb = (-lx > lx - 2 * lR) ? -lx : lx - 2 * lR;
+    int ub = (lx < 2 * lL - lx) ? lx : 2 * lL - lx;
+    double res = 0.0;
+    for (int q = lb; q <= ub; q += 2) {
+        int i = (lx + q) >> 1, j = (lx - q) >> 1;
+        res += orc_binom(lL, i) * orc_binom(lR, j) * pow(dxML, lL - i) * pow(dxMR, lR - j);
+    }
+    return res;
+}
+
+/* computeAxialPGTOrbOverlap, GaussianOrbitals.jl:110-140.  The concentric branch
+ * (:111-117) is the dx -> 0 limit of the general one (:119-127); pow(0,0) = 1 in C as
+ * in Julia, so one body serves both. */
+static double orc_axial_overlap(double xpnSum, double xpnPOS, double xML, double xMR, int iL,
+                                int iR)
+{
+    double dx = xMR - xML;
+    if (iL == 0 && iR == 0) return orc_axial_factor(xpnSum, 0) * exp(-xpnPOS * dx * dx);
+    double res = 0.0;
+    for (int j = 0; j <= (iL + iR) / 2; ++j)
+        res += orc_gauss_prod(xML, xMR, iL, iR, 2 * j) * orc_axial_factor(xpnSum, j);
+    return res * exp(-xpnPOS * dx * dx);
+}
+
+/* computePGTOrbOverlap!, GaussianOrbitals.jl:149-180 */
+double orc_prim_overlap(const double *cen, const double *xpn, const int *ang)
+{
+    double xpnSum = xpn[0] + xpn[1], xpnPOS = xpn[0] * xpn[1] / xpnSum, res = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        double xM = (xpn[0] * cen[d] + xpn[1] * cen[3 + d]) / xpnSum;
+        res *= orc_axial_overlap(xpnSum, xpnPOS, xM - cen[d], xM - cen[3 + d], ang[d],
+                                 ang[3 + d]);
+    }
+    return res;
+}
+
+/* computeAxialPGTOrbCoordDiff!, GaussianOrbitals.jl:253-277: d^degree/dx^degree acting on
+ * the right function, expanded into overlaps with shifted right angular momentum. */
+static double orc_axial_diff(int degree, double xpnL, double xpnR, double xML, double xMR,
+                             int iL, int iR)
+{
+    if (degree < 1) {
+        double s = xpnL + xpnR;
+        return orc_axial_overlap(s, xpnL * xpnR / s, xML, xMR, iL, iR);
+    }
+    double dn = iR < 1 ? 0.0 : orc_axial_diff(degree - 1, xpnL, xpnR, xML, xMR, iL, iR - 1);
+    double up = orc_axial_diff(degree - 1, xpnL, xpnR, xML, xMR, iL, iR + 1);
+    return dn * iR - up * 2.0 * xpnR;
+}
+
+/* kinetic energy: DiagDirectionalDiffSampler with M = 2, direction = -1/2 on every axis
+ * (Samplers.jl:81-89; GaussianOrbitals.jl:322-363, 686-693) */
+double orc_prim_kinetic(const double *cen, const double *xpn, const int *ang)
+{
+    double xpnSum = xpn[0] + xpn[1], xpnPOS = xpn[0] * xpn[1] / xpnSum;
+    double ov[3], df[3];
+    for (int d = 0; d < 3; ++d) {
+        double xM = (xpn[0] * cen[d] + xpn[1] * cen[3 + d]) / xpnSum;
+        double xML = xM - cen[d], xMR = xM - cen[3 + d];
+        ov[d] = orc_axial_overlap(xpnSum, xpnPOS, xML, xMR, ang[d], ang[3 + d]);
+        df[d] = orc_axial_diff(2, xpn[0], xpn[1], xML, xMR, ang[d], ang[3 + d]);
+    }
+    return -0.5 * (df[0] * ov[1] * ov[2] + ov[0] * df[1] * ov[2] + ov[0] * ov[1] * df[2]);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Contracted integrals over the boundary's basis format: flat primitive table + CSR     */
+/* (what MultiOrbitalData holds: OrbitalBases.jl:439-468, Framework.jl:134-153)          */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int64_t nprim, nbf;
+    const double *cen;      /* 3 x nprim, column-major */
+    const double *xpn;      /* nprim */
+    const int32_t *ang;     /* 3 x nprim */
+    const int64_t *bf_off;  /* nbf + 1 */
+    const int64_t *bf_prim; /* 0-based primitive index */
+    const double *bf_w;     /* final weight */
+} orc_basis;
+
+/* getOrbLayoutIntegralCore! two-body, Framework.jl:526-554 (same loop nest, R2 outermost) */
+double orc_eri_quartet(const orc_basis *b, int64_t i, int64_t j, int64_t k, int64_t l)
+{
+    double res = 0.0, cen[12], xpn[4];
+    int ang[12];
+    for (int64_t s = b->bf_off[l]; s < b->bf_off[l + 1]; ++s)
+        for (int64_t r = b->bf_off[k]; r < b->bf_off[k + 1]; ++r) {
+            double w2 = b->bf_w[r] * b->bf_w[s];
+            for (int64_t q = b->bf_off[j]; q < b->bf_off[j + 1]; ++q)
+                for (int64_t p = b->bf_off[i]; p < b->bf_off[i + 1]; ++p) {
+                    int64_t id[4] = {b->bf_prim[p], b->bf_prim[q], b->bf_prim[r], b->bf_prim[s]};
+                    for (int t = 0; t < 4; ++t) {
+                        memcpy(cen + 3 * t, b->cen + 3 * id[t], 3 * sizeof(double));
+                        xpn[t] = b->xpn[id[t]];
+                        for (int d = 0; d < 3; ++d) ang[3 * t + d] = b->ang[3 * id[t] + d];
+                    }
+                    res += orc_prim_eri(cen, xpn, ang) * (b->bf_w[p] * b->bf_w[q] * w2);
+                }
+        }
+    return res;
+}
+
+static inline void orc_tri2(int64_t n, int64_t *i, int64_t *j)
+{   /* convertIndex1DtoTri2D, Iteration.jl:7-12, 0-based here: n -> (i <= j) */
+    int64_t jj = (int64_t)((sqrt(8.0 * (double)(n + 1) - 6.9) - 1.0) / 2.0);
+    while ((jj + 1) * (jj + 2) / 2 <= n) ++jj;
+    while (jj * (jj + 1) / 2 > n) --jj;
+    *j = jj; *i = n - jj * (jj + 1) / 2;
+}
+
+/* getOrbVectorIntegralCore! two-body, Framework.jl:640-665: column-major N^4 tensor,
+ * tensor[i,j,k,l] = (ij|kl), filled from the M(M+1)/2 unique entries and their images.
+ * `parallel` = 0 keeps the reference's serial loop; 1 spreads the unique-entry loop over
+ * OpenMP threads (the values are identical; only used to make fixtures affordable). */
+void orc_eri_tensor(const orc_basis *b, double *T, int parallel)
+{
+    int64_t N = b->nbf, M = N * (N + 1) / 2, U = M * (M + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 64) if (parallel)
+    for (int64_t n = 0; n < U; ++n) {
+        int64_t p, q, i, j, k, l;
+        orc_tri2(n, &p, &q);
+        orc_tri2(p, &i, &j);
+        orc_tri2(q, &k, &l);
+        double v = orc_eri_quartet(b, i, j, k, l);
+#define AT(a, bb, c, d) T[(a) + N * ((bb) + N * ((c) + N * (d)))]
+        AT(i, j, k, l) = v; AT(j, i, k, l) = v; AT(i, j, l, k) = v; AT(j, i, l, k) = v;
+        AT(k, l, i, j) = v; AT(k, l, j, i) = v; AT(l, k, i, j) = v; AT(l, k, j, i) = v;
+#undef AT
+    }
+}
+
+void orc_eri_list(const orc_basis *b, int64_t n, const int64_t *ijkl, double *out, int parallel)
+{
+#pragma omp parallel for schedule(dynamic, 16) if (parallel)
+    for (int64_t t = 0; t < n; ++t)
+        out[t] = orc_eri_quartet(b, ijkl[4 * t], ijkl[4 * t + 1], ijkl[4 * t + 2], ijkl[4 * t + 3]);
+}
+
+/* one-body matrices: kind 0 overlap, 1 kinetic, 2 nuclear attraction (sum_C -Z_C/|r-C|:
+ * GaussianOrbitals.jl:695-707 with the electron charge -1).  Two-index contraction as in
+ * Framework.jl:498-523. out: N x N column-major, Hermitian-filled. */
+void orc_one_body(const orc_basis *b, int kind, int64_t nnuc, const double *Z,
+                  const double *R /*3 x nnuc*/, double *out)
+{
+    int64_t N = b->nbf;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t i = 0; i <= j; ++i) {
+            double res = 0.0, cen[6], xpn[2];
+            int ang[6];
+            for (int64_t q = b->bf_off[j]; q < b->bf_off[j + 1]; ++q)
+                for (int64_t p = b->bf_off[i]; p < b->bf_off[i + 1]; ++p) {
+                    int64_t id[2] = {b->bf_prim[p], b->bf_prim[q]};
+                    for (int t = 0; t < 2; ++t) {
+                        memcpy(cen + 3 * t, b->cen + 3 * id[t], 3 * sizeof(double));
+                        xpn[t] = b->xpn[id[t]];
+                        for (int d = 0; d < 3; ++d) ang[3 * t + d] = b->ang[3 * id[t] + d];
+                    }
+                    double v = 0.0;
+                    if (kind == 0) v = orc_prim_overlap(cen, xpn, ang);
+                    else if (kind == 1) v = orc_prim_kinetic(cen, xpn, ang);
+                    else {
+                        for (int64_t c = 0; c < nnuc; ++c)
+                            v += Z[c] * orc_prim_nuclear(cen, xpn, ang, R + 3 * c);
+                        v = -v;
+                    }
+                    res += v * b->bf_w[p] * b->bf_w[q];
+                }
+            out[i + N * j] = res;
+            out[j + N * i] = res;
+        }
+}
+
+/* getGcore, HartreeFock.jl:305-319: G[mu,nu] = sum DJ[sg,lm] (mu nu|lm sg)
+ *                                            - sum DK[lm,sg] (mu lm|sg nu), mu <= nu,
+ * mirrored.  OpenMP over (mu,nu) stands in for Threads.@threads (:311). */
+void orc_getGcore(int64_t N, const double *H, const double *DJ, const double *DK, double *G)
+{
+    int64_t M = N * (N + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t k = 0; k < M; ++k) {
+        int64_t mu, nu;
+        orc_tri2(k, &mu, &nu);
+        double accJ = 0.0, accK = 0.0;
+        for (int64_t sg = 0; sg < N; ++sg)
+            for (int64_t lm = 0; lm < N; ++lm) {
+                /* dot(transpose(DJ), HeeI[mu,nu,:,:]) : element (lm,sg) pairs with DJ[sg,lm] */
+                accJ += DJ[sg + N * lm] * H[mu + N * (nu + N * (lm + N * sg))];
+                /* dot(DK, HeeI[mu,:,:,nu]) : element (lm,sg) pairs with DK[lm,sg] */
+                accK += DK[lm + N * sg] * H[mu + N * (lm + N * (sg + N * nu))];
+            }
+        G[mu + N * nu] = accJ - accK;
+        G[nu + N * mu] = accJ - accK;
+    }
+}

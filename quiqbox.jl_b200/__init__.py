@@ -1,0 +1,5 @@
+"""B200-native ERI + Fock-build engine behind Quiqbox.jl's API (host-side mirror)."""
+from .basis import (GTO, MultiOrbitalData, NuclearCluster, SubshellXYZs, genGaussTypeOrb,
+                    genGaussTypeOrbSeq, get3DimPGTOrbNormFactor, nucRepulsion)
+from .hartreefock import (HFconfig, HFfinalInfo, RCHartreeFock, SCFconfig, UOHartreeFock,
+                          runHartreeFockCore)

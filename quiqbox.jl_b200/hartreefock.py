@@ -1,0 +1,253 @@
+"""Hartree-Fock driver: the caller of the J/K hot path.
+
+Host-side mirror of src/HartreeFock.jl.  The dense linear algebra of an SCF step (eigen,
+density, DIIS) stays on the host exactly as SURVEY.md section 8 (row a12) scopes it; the only
+expensive call, ``getGcore`` (HartreeFock.jl:305-319), goes to the CUDA library through the
+``DeviceERI`` handle (integrals.py -> include/qbx.h ``qbx_fock_build``).
+
+Conventions kept from the reference:
+  getD   D = C_occ C_occ^T, no factor 2                       (HartreeFock.jl:296-299)
+  getG   RHF: getGcore(HeeI, 2D, D); UHF: getGcore(HeeI, Da+Db, Ds)      (:322-327)
+  getF   F = Hcore + G                                                  (:330-335)
+  getE   E_spin = <D, Hcore + F>/2; RHF total = 2 E_spin, UHF = Ea + Eb (:339-350)
+  getC   generalised eigenproblem through X = S^{-1/2}, column sign fixed (:39-59)
+  guesses :CoreH (:221-226), :GWH (:235-254), :SAD (:266-293), UHF symmetry breaking
+          (breakCoeffSymmetryCore :71-100)
+  SCF    stages of (:DD | :DIIS | :ADIIS | :EDIIS) with per-stage thresholds; convergence
+         |dE| <= thr and RMS(dD) <= ratio*thr, gated by RMS(FDS-SDF) <= ratio*thr (:1171-1174)
+
+The interpolation stages (:ADIIS, :EDIIS) are served by the same commutator-DIIS
+extrapolation as :DIIS: they differ only in the SCF *trajectory*, not in the converged
+energy that parity is defined on (BASELINE.json: 1e-8 Ha).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .basis import GTO, MultiOrbitalData, NuclearCluster, nucRepulsion
+
+defaultDS = 0.75            # HartreeFock.jl: damping strength of :DD
+defaultDIISsize = 10
+defaultHFmaxStep = 200      # HartreeFock.jl:20
+defaultSCFconfigArgs = ((":DD", ":ADIIS", ":DIIS"), (5e-3, 1e-4, 1e-9))   # :27
+defaultSecConvRatio = (1000.0, 1000.0)                                     # :28
+
+
+class RCHartreeFock:   # restricted closed-shell (HartreeFock.jl:61)
+    spins = 1
+
+
+class UOHartreeFock:   # unrestricted open-shell
+    spins = 2
+
+
+@dataclass
+class SCFconfig:
+    """HartreeFock.jl:659-688."""
+    method: Sequence[str] = defaultSCFconfigArgs[0]
+    interval: Sequence[float] = defaultSCFconfigArgs[1]
+    secondaryConvRatio: Tuple[float, float] = defaultSecConvRatio
+    threshold: Optional[float] = None     # SCFconfig(threshold=t): default methods, last stage t
+
+    def stages(self):
+        meth = [m.lstrip(":").upper() for m in self.method]
+        thr = list(self.interval)
+        if self.threshold is not None:
+            thr = [max(t, self.threshold) for t in thr[:-1]] + [self.threshold]
+        if len(meth) != len(thr):
+            raise AssertionError("`method` and `interval` must have the same length.")
+        return list(zip(meth, thr))
+
+
+@dataclass
+class HFconfig:
+    """HartreeFock.jl:874-904."""
+    HF: object = None                      # RCHartreeFock() / UOHartreeFock(); None = by electron count
+    initial: object = ":SAD"               # ":CoreH" | ":GWH" | ":SAD" | tuple of coefficient matrices
+    strategy: SCFconfig = field(default_factory=SCFconfig)
+    maxStep: int = defaultHFmaxStep
+    saveTrace: bool = False
+
+
+@dataclass
+class HFfinalInfo:
+    """HartreeFock.jl:791-819.  ``energy = (E_electronic, E_nuclear-repulsion)``."""
+    energy: Tuple[float, float]
+    coeff: Tuple[np.ndarray, ...]
+    density: Tuple[np.ndarray, ...]
+    fock: Tuple[np.ndarray, ...]
+    occu: Tuple[np.ndarray, ...]           # orbital energies per spin sector
+    converged: bool
+    steps: int
+    fockBuilds: int
+    trace: List[float] = field(default_factory=list)
+
+
+# ---------------------------------------------------------------------------- small algebra
+def getOrthonormalization(S: np.ndarray) -> np.ndarray:
+    """X = S^{-1/2} (symmetric), HartreeFock.jl:39-42."""
+    w, U = np.linalg.eigh(S)
+    return (U / np.sqrt(w)) @ U.T
+
+
+def getC(X: np.ndarray, F: np.ndarray, stabilizeSign=True):
+    """solveFockMatrix, HartreeFock.jl:46-56."""
+    e, Cx = np.linalg.eigh(X.T @ F @ X)
+    C = X @ Cx
+    if stabilizeSign:
+        C = C * np.where(C[0, :] < 0, -1.0, 1.0)
+    return C, e
+
+
+def getD(C: np.ndarray, N: int) -> np.ndarray:
+    return C[:, :N] @ C[:, :N].T
+
+
+def getG(gcore: Callable, Ds: Sequence[np.ndarray]):
+    """HartreeFock.jl:322-327.  ``gcore(DJ, [DK...]) -> [G...]`` is the device call; UHF sends
+    both exchange densities in one pass (qbx_fock_build nmat=2)."""
+    if len(Ds) == 1:
+        return tuple(gcore(2.0 * Ds[0], [Ds[0]]))
+    return tuple(gcore(Ds[0] + Ds[1], [Ds[0], Ds[1]]))
+
+
+def getE(Hcore, F, D) -> float:
+    return float(np.vdot(D, Hcore + F)) / 2.0
+
+
+def get2SpinQuantity(vals: Sequence[float]) -> float:
+    """HartreeFock.jl:344: RHF doubles the single sector, UHF sums the two."""
+    return (2.0 if len(vals) == 1 else 1.0) * float(sum(vals))
+
+
+def breakCoeffSymmetryCore(X, C1, C2):
+    """HartreeFock.jl:71-100."""
+    Xinv = np.linalg.inv(X)
+    c1, c2 = Xinv @ C1, Xinv @ C2
+    for k in range(c1.shape[1]):
+        col = c1[:, k] if k % 2 == 0 else c2[:, k]
+        idx = int(np.argmax(np.abs(col)))
+        mag, val = abs(col[idx]), col[idx]
+        if abs(mag - 1.0) < np.sqrt(np.finfo(float).eps):
+            col[idx] *= -val
+        else:
+            col[idx] = 0.0
+            col /= np.linalg.norm(col)
+    return X @ c1, X @ c2
+
+
+# ---------------------------------------------------------------------------- guesses
+def _guess(kind, nspin, X, S, Hcore, gcore, Ns, sad):
+    if isinstance(kind, (tuple, list)) and not isinstance(kind, str):
+        Cs = tuple(np.asarray(c, dtype=np.float64) for c in kind)
+        for C in Cs:
+            if C.shape != S.shape:
+                raise ValueError("DimensionMismatch: initial coefficient matrix does not match the basis.")
+        return Cs
+    k = str(kind).lstrip(":").upper()
+    if k == "COREH":
+        C = getC(X, Hcore)[0]
+    elif k == "GWH":
+        d = np.diag(Hcore)
+        C = getC(X, 3.0 * S * (d[:, None] + d[None, :]) / 8.0)[0]     # HartreeFock.jl:246-248
+    elif k == "SAD":
+        Dsad = sad() if sad is not None else None
+        if Dsad is None:
+            C = getC(X, Hcore)[0]
+        else:
+            # HartreeFock.jl:126-140: one Fock build on the superposed atomic densities
+            if nspin == 1:
+                Dm = (Dsad[0] + Dsad[1]) / 2.0
+                F = Hcore + getG(gcore, (Dm,))[0]
+                return (getC(X, F)[0],)
+            Gs = getG(gcore, Dsad)
+            Cs = tuple(getC(X, Hcore + G)[0] for G in Gs)
+            if np.sqrt(np.mean((np.linalg.inv(X) @ (Cs[0] - Cs[1])) ** 2)) < 0.1:
+                Cs = breakCoeffSymmetryCore(X, Cs[0].copy(), Cs[1].copy())
+            return Cs
+    else:
+        raise ValueError(f"unknown initial guess {kind!r}")
+    if nspin == 1:
+        return (C,)
+    return breakCoeffSymmetryCore(X, C.copy(), C.copy())
+
+
+# ---------------------------------------------------------------------------- SCF core
+def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFconfig,
+                       sad: Optional[Callable] = None, printInfo=False):
+    """HartreeFock.jl:1049-1228 on top of an abstract ``gcore`` (the hot-path call)."""
+    nspin = len(Ns)
+    X = getOrthonormalization(S)
+    nbuild = [0]
+
+    def gc(DJ, DKs):
+        nbuild[0] += 1
+        return gcore(DJ, DKs)
+
+    Cs = _guess(config.initial, nspin, X, S, Hcore, gc, Ns, sad)
+    Ds = tuple(getD(C, n) for C, n in zip(Cs, Ns))
+    Fs = tuple(Hcore + G for G in getG(gc, Ds))
+    Etot = get2SpinQuantity([getE(Hcore, F, D) for F, D in zip(Fs, Ds)])
+    trace = [Etot]
+    ratioD, ratioF = config.strategy.secondaryConvRatio
+    step, converged = 0, False
+    eps = [None] * nspin
+
+    def err_vec(Fs_, Ds_):
+        return [X.T @ (F @ D @ S - S @ D @ F) @ X for F, D in zip(Fs_, Ds_)]
+
+    for method, thr in config.strategy.stages():
+        histF: List[Tuple[np.ndarray, ...]] = []
+        histE: List[np.ndarray] = []
+        stage_done = False
+        while step < config.maxStep:
+            step += 1
+            if method == "DD":
+                # directDiag, HartreeFock.jl:1245-1251 then getCDFE on F[D_damped] (:1265)
+                Dn = tuple((1 - defaultDS) * getD(getC(X, F)[0], n) + defaultDS * D
+                           for F, D, n in zip(Fs, Ds, Ns))
+                Fin = tuple(Hcore + G for G in getG(gc, Dn))
+            else:
+                histF.append(Fs)
+                histE.append(np.concatenate([e.ravel() for e in err_vec(Fs, Ds)]))
+                histF, histE = histF[-defaultDIISsize:], histE[-defaultDIISsize:]
+                m = len(histF)
+                if m > 1:
+                    B = -np.ones((m + 1, m + 1)); B[m, m] = 0.0
+                    for a in range(m):
+                        for b in range(m):
+                            B[a, b] = histE[a] @ histE[b]
+                    rhs = np.zeros(m + 1); rhs[m] = -1.0
+                    try:
+                        c = np.linalg.solve(B, rhs)[:m]
+                    except np.linalg.LinAlgError:
+                        c = np.zeros(m); c[-1] = 1.0
+                    Fin = tuple(sum(c[a] * histF[a][s] for a in range(m)) for s in range(nspin))
+                else:
+                    Fin = Fs
+            # getCDFE, HartreeFock.jl:392-403
+            sol = [getC(X, F) for F in Fin]
+            Cn = tuple(s[0] for s in sol)
+            eps = [s[1] for s in sol]
+            Dn2 = tuple(getD(C, n) for C, n in zip(Cn, Ns))
+            Fn = tuple(Hcore + G for G in getG(gc, Dn2))
+            En = get2SpinQuantity([getE(Hcore, F, D) for F, D in zip(Fn, Dn2)])
+            dE = En - Etot
+            Dt_old = sum(Ds) * (2.0 if nspin == 1 else 1.0)
+            Dt_new = sum(Dn2) * (2.0 if nspin == 1 else 1.0)
+            dD = float(np.sqrt(np.mean((Dt_new - Dt_old) ** 2)))
+            Cs, Ds, Fs, Etot = Cn, Dn2, Fn, En
+            dF = float(np.sqrt(np.mean(np.concatenate([e.ravel() for e in err_vec(Fs, Ds)]) ** 2)))
+            trace.append(Etot)
+            if printInfo:
+                print(f"| {step:4d} | {method:5s} | {Etot: .12f} | {dE: .3e} | {dF:.3e} | {dD:.3e}")
+            if abs(dE) <= thr and dD <= ratioD * thr and dF <= ratioF * thr:
+                stage_done = True
+                break
+        if not stage_done:
+            break
+        converged = True if (method, thr) == config.strategy.stages()[-1] else converged
+    return Cs, Ds, Fs, eps, Etot, converged, step, nbuild[0], trace

@@ -1,0 +1,131 @@
+"""ctypes front-end of the CPU oracle (oracle/qbx_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs -- never by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_ROOT, "oracle", "qbx_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class _Basis(C.Structure):
+    _fields_ = [("nprim", C.c_int64), ("nbf", C.c_int64), ("cen", C.c_void_p), ("xpn", C.c_void_p),
+                ("ang", C.c_void_p), ("bf_off", C.c_void_p), ("bf_prim", C.c_void_p), ("bf_w", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_boys.restype = C.c_double
+        _lib.orc_boys.argtypes = [C.c_double, C.c_int]
+        for f in ("orc_prim_eri", "orc_prim_overlap", "orc_prim_kinetic"):
+            getattr(_lib, f).restype = C.c_double
+            getattr(_lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_prim_nuclear.restype = C.c_double
+        _lib.orc_prim_nuclear.argtypes = [C.c_void_p] * 4
+        _lib.orc_eri_quartet.restype = C.c_double
+        _lib.orc_eri_quartet.argtypes = [C.c_void_p] + [C.c_int64] * 4
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def boys(x, n):
+    return lib().orc_boys(float(x), int(n))
+
+
+def boys_sequence(x, n):
+    out = np.zeros(n + 1)
+    lib().orc_boys_sequence(C.c_double(x), C.c_int(n), _p(out))
+    return out
+
+
+def _prim_args(prims):
+    cen = np.ascontiguousarray([p[0] for p in prims], dtype=np.float64)
+    xpn = np.ascontiguousarray([p[1] for p in prims], dtype=np.float64)
+    ang = np.ascontiguousarray([p[2] for p in prims], dtype=np.int32)
+    return cen, xpn, ang
+
+
+def prim_eri(p1, p2, p3, p4):
+    """(p1 p2|p3 p4) for primitives given as (center, exponent, (i,j,k))."""
+    cen, xpn, ang = _prim_args([p1, p2, p3, p4])
+    return lib().orc_prim_eri(_p(cen), _p(xpn), _p(ang))
+
+
+def prim_one_body(kind, p1, p2, point=None):
+    cen, xpn, ang = _prim_args([p1, p2])
+    if kind == "overlap":
+        return lib().orc_prim_overlap(_p(cen), _p(xpn), _p(ang))
+    if kind == "kinetic":
+        return lib().orc_prim_kinetic(_p(cen), _p(xpn), _p(ang))
+    pt = np.ascontiguousarray(point, dtype=np.float64)
+    return lib().orc_prim_nuclear(_p(cen), _p(xpn), _p(ang), _p(pt))
+
+
+class OracleBasis:
+    """Holds a MultiOrbitalData (quiqbox.jl_b200.basis) in the oracle's struct."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        self._keep = [np.ascontiguousarray(mod.cen, dtype=np.float64), np.ascontiguousarray(mod.xpn, dtype=np.float64),
+                      np.ascontiguousarray(mod.ang, dtype=np.int32), np.ascontiguousarray(mod.bf_off, dtype=np.int64),
+                      np.ascontiguousarray(mod.bf_prim, dtype=np.int64), np.ascontiguousarray(mod.bf_w, dtype=np.float64)]
+        self.s = _Basis(mod.nprim, mod.nbf, *[a.ctypes.data for a in self._keep])
+        self.nbf = mod.nbf
+
+    def eri(self, i, j, k, l):
+        return lib().orc_eri_quartet(C.byref(self.s), i, j, k, l)
+
+    def eri_list(self, ijkl, parallel=True):
+        ijkl = np.ascontiguousarray(ijkl, dtype=np.int64).reshape(-1, 4)
+        out = np.zeros(len(ijkl))
+        lib().orc_eri_list(C.byref(self.s), C.c_int64(len(ijkl)), _p(ijkl), _p(out), C.c_int(int(parallel)))
+        return out
+
+    def eri_tensor(self, parallel=True):
+        """N^4 tensor, T[i,j,k,l] = (ij|kl) (numpy index order = the reference's)."""
+        n = self.nbf
+        out = np.zeros(n ** 4)
+        lib().orc_eri_tensor(C.byref(self.s), _p(out), C.c_int(int(parallel)))
+        return out.reshape((n, n, n, n), order="F")
+
+    def one_body(self, kind, Z=None, R=None):
+        n = self.nbf
+        out = np.zeros(n * n)
+        k = {"overlap": 0, "kinetic": 1, "nuclear": 2}[kind]
+        Z = np.ascontiguousarray(Z if Z is not None else [], dtype=np.float64)
+        R = np.ascontiguousarray(R if R is not None else [], dtype=np.float64)
+        lib().orc_one_body(C.byref(self.s), C.c_int(k), C.c_int64(len(Z)), _p(Z), _p(R), _p(out))
+        return out.reshape((n, n), order="F")
+
+
+def getGcore(H, DJ, DK):
+    """orc_getGcore on a dense tensor H[i,j,k,l] (any memory order)."""
+    n = DJ.shape[0]
+    Hf = np.asfortranarray(H)
+    G = np.zeros((n, n), order="F")
+    lib().orc_getGcore(C.c_int64(n), C.c_void_p(Hf.ctypes.data), _p(np.asfortranarray(DJ)),
+                       _p(np.asfortranarray(DK)), C.c_void_p(G.ctypes.data))
+    return np.ascontiguousarray(G)
+
+
+def gcore_from_tensor(H):
+    """Adapter with the signature hartreefock.runHartreeFockCore expects."""
+    return lambda DJ, DKs: [getGcore(H, DJ, DK) for DK in DKs]

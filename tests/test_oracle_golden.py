@@ -1,0 +1,151 @@
+"""Pins the CPU oracle (oracle/qbx_oracle.c) to every known-answer vector the reference's
+own tests hold for the hot path.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+import quiqbox_b200 as qb
+from molecules import h2, h2o2, hoh_linear
+
+RTOL = np.sqrt(np.finfo(float).eps)        # the reference's `isapprox` default, rtol = sqrt(eps)
+
+# test/unit-tests/Integration/BoysFunction-test.jl:6-22
+BOYS_POINTS = [
+    (2.6e-7, 100, 4.97512309732144e-03), (6.4e-5, 45, 1.09883228385254e-02),
+    (1.4e-3, 20, 2.43577075309547e-02), (6.4, 25, 4.28028518677348e-05),
+    (13.0, 25, 8.45734447905704e-08), (26.0, 30, 3.57321060811178e-13),
+    (27.0, 15, 1.08359515555596e-11), (30.0, 20, 1.37585444267909e-13),
+    (33.0, 100, 3.42689684943483e-17), (50.0, 16, 2.40509456111904e-16),
+    (50.0, 64, 5.67024356263279e-24), (85.0, 33, 1.74268831008018e-29),
+    (100.0, 36, 3.08919970425521e-33), (120.0, 100, 4.97723065221079e-53),
+    (125.1, 100, 7.75391047694625e-55)]
+
+
+@pytest.mark.parametrize("x,n,val", BOYS_POINTS)
+def test_boys_points(x, n, val):
+    assert oracle.boys(x, n) == pytest.approx(val, rel=RTOL)
+
+
+def test_boys_sequence():
+    # BoysFunction-test.jl:30-32
+    f = oracle.boys_sequence(50.0, 100)
+    assert f[16] == pytest.approx(BOYS_POINTS[9][2], rel=RTOL)
+    assert f[64] == pytest.approx(BOYS_POINTS[10][2], rel=RTOL)
+
+
+# test/unit-tests/Integration/Coulomb-test.jl:9-14, 48-49
+G = {1: ((0.1, 0.2, 0.3), 2.0, (1, 7, 2)), 2: ((0.1, 0.2, 0.3), 2.0, (1, 1, 0)),
+     3: ((0.1, 0.2, 0.3), 2.0, (0, 0, 0)), 4: ((0.3, 0.1, 0.5), 2.0, (0, 0, 0)),
+     5: ((0.3, 0.1, 0.5), 2.0, (2, 0, 0)), 6: ((0.1, 0.2, 0.3), 2.0, (2, 0, 0)),
+     7: ((0.9, 0.6, 0.1), 2.5, (1, 1, 0)), 8: ((0.6, 0.7, 0.8), 3.0, (3, 1, 2))}
+
+
+@pytest.mark.parametrize("pair,val", [((1, 2), 0.00021406291700540685), ((1, 1), 0.00016035624620095473),
+                                      ((3, 3), 1.3209276479060006), ((3, 4), 1.102953813735257),
+                                      ((3, 5), 0.1305787950084035), ((6, 3), 0.11995218441914622),
+                                      ((3, 6), 0.11995218441914622)])
+def test_prim_one_body_coulomb(pair, val):
+    # Coulomb-test.jl:32-45
+    a, b = pair
+    assert oracle.prim_one_body("nuclear", G[a], G[b], (0.0, 0.0, 0.0)) == pytest.approx(val, rel=RTOL)
+
+
+@pytest.mark.parametrize("quartets,val", [
+    ([(1, 1, 2, 2), (2, 2, 1, 1)], 1.7675350484831864e-6),
+    ([(1, 2, 1, 2), (1, 2, 2, 1), (2, 1, 2, 1)], 6.267963629018787e-8),
+    ([(3, 3, 4, 4), (4, 4, 3, 3)], 0.7291219052871128),
+    ([(1, 4, 7, 8), (4, 1, 7, 8), (4, 1, 8, 7), (1, 4, 8, 7), (7, 8, 1, 4), (8, 7, 1, 4), (8, 7, 4, 1),
+      (7, 8, 4, 1)], -2.4175946692430508e-9)])
+def test_prim_two_body(quartets, val):
+    # Coulomb-test.jl:56-81, all listed permutational images
+    for a, b, c, d in quartets:
+        assert oracle.prim_eri(G[a], G[b], G[c], G[d]) == pytest.approx(val, rel=RTOL)
+
+
+def _lih():
+    # Coulomb-test.jl:118-135
+    gen = qb.genGaussTypeOrb
+    x = (1.4, 0.0, 0.0)
+    li = [0.6362897469, 0.1478600533, 0.0480886784]
+    p = [0.1559162750, 0.6076837186, 0.3919573931]
+    return [gen((0., 0., 0.), [3.425250914, 0.6239137298, 0.1688554040],
+                [0.1543289673, 0.5353281423, 0.4446345422], innerRenormalize=True),
+            gen(x, [16.11957475, 2.93620066, 0.7946504870], [0.1543289673, 0.5353281423, 0.4446345422],
+                innerRenormalize=True),
+            gen(x, li, [-0.09996722919, 0.3995128261, 0.7001154689], innerRenormalize=True),
+            gen(x, li, p, (1, 0, 0), innerRenormalize=True), gen(x, li, p, (0, 1, 0), innerRenormalize=True),
+            gen(x, li, p, (0, 0, 1), innerRenormalize=True)]
+
+
+def test_lih_nuclear_attraction_and_eri_symmetry():
+    # Coulomb-test.jl:139-154
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(_lih()))
+    V2 = ob.one_body("nuclear", Z=[1.0, 3.0], R=[(0., 0., 0.), (1.4, 0., 0.)])
+    ref = [-3.1880952107948826, -1.9932525008344286, -1.4155676040098832, 1.2630060649812684, 0.0, 0.0,
+           -1.9932525008344286, -8.6953599854861, -1.1279531550756718, 0.05959228438098337, 0.0, 0.0,
+           -1.4155676040098832, -1.1279531550756718, -1.5854895488805438, 0.1297201051017447, 0.0, 0.0,
+           1.2630060649812684, 0.05959228438098337, 0.1297201051017447, -1.637219301724801, 0.0, 0.0,
+           0.0, 0.0, 0.0, 0.0, -1.546580055447794, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1.546580055447794]
+    assert np.allclose(V2.ravel(order="F"), ref, rtol=RTOL, atol=1e-14)
+    T = ob.eri_tensor()
+    for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 0, 1), (2, 3, 1, 0), (3, 2, 1, 0)]:
+        assert np.array_equal(T, T.transpose(perm))
+
+
+def test_li_321g_overlap_normalisation():
+    # OrbitalBases-test.jl: genGaussTypeOrbSeq(:Li, "3-21G") overlap -> diagonal must be 1 for
+    # the s functions built from normalised primitives with contraction coefficients
+    bs = qb.genGaussTypeOrbSeq((0.0, 0.0, 0.0), "H", "STO-3G")
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs))
+    assert ob.one_body("overlap")[0, 0] == pytest.approx(1.0, abs=1e-6)
+
+
+def _scf(nuc, coords, basis, hf, initial=":CoreH", thr=None, maxStep=200):
+    cluster = qb.NuclearCluster(nuc, coords)
+    bs = sum((qb.genGaussTypeOrbSeq(c, s, basis) for s, c in zip(nuc, coords)), [])
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs))
+    S = ob.one_body("overlap")
+    H = ob.one_body("kinetic") + ob.one_body("nuclear", Z=cluster.charges, R=cluster.coordArray)
+    T = ob.eri_tensor()
+    ne = int(cluster.charges.sum())
+    Ns = (ne // 2,) if hf == "RHF" else (ne - ne // 2, ne // 2)
+    strat = qb.SCFconfig() if thr is None else qb.SCFconfig(threshold=thr, secondaryConvRatio=(5, 5))
+    cfg = qb.HFconfig(initial=initial, strategy=strat, maxStep=maxStep)
+    out = qb.runHartreeFockCore(S, H, oracle.gcore_from_tensor(T), Ns, cfg)
+    return out, qb.nucRepulsion(cluster), (S, H, T)
+
+
+def test_hoh_sto3g_rhf_uhf():
+    # HartreeFock-test.jl:12-16, 92, 111-128, 152
+    (Cs, Ds, Fs, eps, E, conv, *_), _, (S, H, T) = _scf(*hoh_linear(), "STO-3G", "RHF")
+    assert conv and E == pytest.approx(-93.7878386328627, abs=7.5e-8)
+    Fref = np.array([[-2.255358688, -1.960982029, -4.484369214, -2.511689786, 0.483603806, 0, 0],
+                     [-1.960982029, -2.255358688, -4.484369214, -2.511689786, -0.483603806, 0, 0],
+                     [-4.484369214, -4.484369214, -20.920383179, -5.363456843, 0, 0, 0],
+                     [-2.511689786, -2.511689786, -5.363456843, -2.896377602, 0, 0, 0],
+                     [0.483603806, -0.483603806, 0, 0, -1.280927053, 0, 0],
+                     [0, 0, 0, 0, 0, -0.661307596, 0], [0, 0, 0, 0, 0, 0, -0.661307596]])
+    assert np.allclose(Fs[0], Fref, atol=7.5e-7)
+    assert np.allclose(eps[0], [-20.930384473, -1.616675719, -1.284466204, -0.661307596, -0.661307596,
+                                1.060815281, 1.847804072], atol=7.5e-7)
+    assert np.allclose(Ds[0] @ S @ Ds[0], Ds[0], atol=7.5e-8)
+    (_, _, _, _, Eu, convu, *_), _, _ = _scf(*hoh_linear(), "STO-3G", "UHF")
+    assert convu and Eu == pytest.approx(-93.78783863286264, abs=7.5e-8)
+
+
+# HartreeFock-test.jl:221-258 (every 7th point keeps the CPU suite short; all 100 are in
+# tests/golden/h2_321g_curve.json and checked against the CUDA path in the gpu tests)
+def test_h2_321g_curve():
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "h2_321g_curve.json")))
+    for k in range(0, 100, 7):
+        R = 0.1 + 0.2 * k
+        for hf, key in (("RHF", "rhfs"), ("UHF", "uhfs")):
+            (_, _, _, _, E, conv, *_), Enn, _ = _scf(*h2(R), "3-21G", hf, maxStep=300)
+            assert E + Enn == pytest.approx(g[key][k], abs=7.5e-7), (R, hf)
+
+
+def test_h2o2_631g():
+    # HartreeFock-test.jl:294-352
+    (_, _, _, _, E, conv, *_), _, _ = _scf(*h2o2(), "6-31G", "RHF", thr=5e-10)
+    assert conv and E == pytest.approx(-187.42063898359095, abs=2.5e-9)
