@@ -1,0 +1,125 @@
+/*
+ * qbx.h -- C ABI of the B200-native ERI + Fock-build engine behind Quiqbox.jl.
+ *
+ * The reference (frankwswang/Quiqbox.jl v0.6.3) is pure Julia and has no FFI of its own;
+ * the seams this library plugs into are two Julia methods:
+ *
+ *   seam 1  getOrbVectorIntegralCore!(::TwoBodyOrbIntegralInfo{T,3,T,<:CoulombInteractionSampler}, ptrVector)
+ *           src/Integration/Framework.jl:640-698  (+ getOrbLayoutIntegralCore! :526-554)
+ *   seam 2  getGcore(HeeI::AbstractArray{T,4}, DJ, DK)          src/HartreeFock.jl:305-319
+ *
+ * Everything is extern "C", plain pointers and sizes.  Every function returns 0 on success
+ * and a non-zero code on failure, with text available from qbx_last_error(); no exception
+ * crosses the boundary and the library never calls back into the host language.  Host
+ * arrays belong to the caller and are only read/written during the call.  All device state
+ * lives behind the opaque qbx_basis handle.  One process drives one GPU (qbx_init selects
+ * it); multi-GPU runs are one process per GPU, each holding the shard (rank, nranks) of the
+ * shell-quartet list, and sum their partial G matrices with an all-reduce (NCCL).
+ *
+ * Array conventions are the reference's: column-major, chemists' notation,
+ * tensor[i,j,k,l] = (ij|kl), 0-based indices at this boundary.
+ */
+#ifndef QBX_H
+#define QBX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qbx_basis qbx_basis;
+
+/* error codes */
+enum { QBX_OK = 0, QBX_ERR_ARG = 1, QBX_ERR_CUDA = 2, QBX_ERR_STATE = 3, QBX_ERR_RANGE = 4, QBX_ERR_NOMEM = 5 };
+
+/* Select and initialise CUDA device `device` for this process (idempotent).  n_dev_out (may
+ * be NULL) receives the number of visible devices.  No reference counterpart (the reference
+ * has no device); called once from the Julia glue's __init__. */
+int qbx_init(int device, int *n_dev_out);
+int qbx_shutdown(void);
+const char *qbx_last_error(void);
+
+/* Basis ingestion = what MultiOrbitalData holds (src/OrbitalBases.jl:439-468) after
+ * getOrbCorePointers/buildOrbCoreWeight! folded normalisation into the weights
+ * (src/Integration/Framework.jl:748-817): a de-duplicated table of primitive Cartesian
+ * Gaussians x^i y^j z^k exp(-xpn r^2) (prepareOrbitalInfoCore,
+ * src/Integration/Engines/GaussianOrbitals.jl:65-78) and, per basis function, a CSR list of
+ * (primitive index, final weight) (OrbCorePointer, Framework.jl:134-153).
+ *   cen  3 x nprim column-major, xpn nprim, ang 3 x nprim,
+ *   bf_off nbf+1 (0-based CSR), bf_prim / bf_w  bf_off[nbf] entries.
+ * Shells are reconstructed inside (functions that share centre, exponents and radial
+ * coefficients up to a per-component factor); functions that do not factor into shells
+ * are kept as generic single functions. */
+int qbx_basis_create(int64_t nprim, const double *cen, const double *xpn, const int32_t *ang,
+                     int64_t nbf, const int64_t *bf_off, const int64_t *bf_prim, const double *bf_w,
+                     qbx_basis **out);
+int qbx_basis_destroy(qbx_basis *b);
+
+/* info[0..15]: nbf, nshell, max l, class-path usable (1/0), n shell pairs, n unique shell
+ * quartets in this rank's shard (after screening), n unique contracted ERI values in the
+ * shard, stored bytes, n primitive quartets evaluated, rest reserved (0). */
+int qbx_basis_info(qbx_basis *b, int64_t *info);
+
+/* seam 1, whole tensor: = elecRepulsions(bs) (src/Integration/Interface.jl:356-365 ->
+ * getOrbVectorIntegralCore!, Framework.jl:640-698).  out: host, nbf^4 doubles, column-major,
+ * all 8 permutational images written.  Fails without writing if out_bytes < nbf^4 * 8. */
+int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes);
+
+/* seam 1, single entries: = elecRepulsion(a,b,c,d) (Interface.jl:331-342 ->
+ * getOrbLayoutIntegralCore!, Framework.jl:526-554).  ijkl: 4 x n, 0-based function indices;
+ * any angular momentum (generic per-function kernel). */
+int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, double *out);
+
+/* Build this rank's device-resident ERI representation for repeated Fock builds: what
+ * initializeHartreeFock obtains at src/HartreeFock.jl:189-191 and stores in
+ * ElecHamiltonianConfig.twoBody (:143-151).
+ *   screen_tol  Schwarz threshold on sqrt((ab|ab)(cd|cd)); 0 disables screening
+ *   mode        0 = stored (packed unique ERIs kept in HBM), 1 = direct (recomputed in
+ *               every qbx_fock_build), 2 = dense N^4 tensor (small N / irregular bases)
+ *   rank,nranks shard of the cost-balanced shell-quartet list owned by this process */
+int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank, int nranks);
+
+/* seam 2: = getGcore(HeeI, DJ, DK_m) for m = 0..nmat-1 sharing one DJ
+ * (src/HartreeFock.jl:305-327; RHF nmat = 1 with DJ = 2D, DK = D; UHF nmat = 2 with
+ * DJ = Da+Db, DK = Da, Db).  DJ: nbf^2, DK and G: nbf^2 * nmat, column-major, host.
+ * G is Hermitian-filled.  With nranks > 1 the result is this rank's PARTIAL G; the caller
+ * sums over ranks (torch.distributed / NCCL all-reduce). */
+int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const double *DK, double *G);
+
+/* Same, device pointers and a caller stream (cudaStream_t as void*; NULL = the library's
+ * stream); asynchronous with respect to the host.  This is what the multi-GPU host code
+ * feeds straight into the NCCL all-reduce. */
+int qbx_fock_build_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG,
+                          void *stream);
+
+/* Recompute this rank's shard of unique ERIs into the packed store (the ERI-throughput
+ * step bench.py times).  Synchronous. */
+int qbx_eri_recompute(qbx_basis *b);
+
+/* One-electron matrices needed to close an SCF (the first "next" row):
+ * kind 0 overlap, 1 kinetic, 2 nuclear attraction (src/Integration/Interface.jl:46-312;
+ * engines GaussianOrbitals.jl:94-363, 478-522).  Z: nnuc charges, R: 3 x nnuc. out: nbf^2. */
+int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *Z, const double *R, double *out);
+
+/* Boys function in isolation: out[(mmax+1)*t + m] = F_m(T[t])
+ * (computeBoysSequence, src/Integration/Engines/BoysFunction.jl:67-77).
+ * table != 0 uses the tabulated fast path of the class kernels (mmax <= 8). */
+int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
+
+/* Synthetic throughput sweep: nquartets contracted shell quartets of class
+ * (la lb|lc ld) with uniform contraction degree K, generated from `seed` (centres uniform in
+ * a 10-bohr cube, exponents log-uniform in [0.1,1e3], coefficients in [-1,1]).  secs: device
+ * time of the ERI kernel, checksum: sum of all values.  sample_out (may be NULL): the first
+ * min(nsample, nquartets) quartets' values and sample_geom their inputs, for oracle checks. */
+int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed,
+                   double *secs, double *checksum, int64_t nsample, double *sample_out, double *sample_geom);
+
+/* counters since the last reset: [0] kernels launched, [1] device seconds in ERI kernels,
+ * [2] device seconds in digestion kernels, [3] primitive quartets evaluated,
+ * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */
+int qbx_stats(qbx_basis *b, double *out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -3,3 +3,6 @@ from .basis import (GTO, MultiOrbitalData, NuclearCluster, SubshellXYZs, genGaus
                     genGaussTypeOrbSeq, get3DimPGTOrbNormFactor, nucRepulsion)
 from .hartreefock import (HFconfig, HFfinalInfo, RCHartreeFock, SCFconfig, UOHartreeFock,
                           runHartreeFockCore)
+from .hartreefock import runHartreeFock
+from .integrals import (DeviceBasis, DeviceERI, boys, coreHamiltonian, elecKinetics, elecRepulsion,
+                        elecRepulsionList, elecRepulsions, getGcore, nucAttractions, overlaps)

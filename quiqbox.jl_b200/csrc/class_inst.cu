@@ -1,0 +1,33 @@
+// One translation unit per quartet class: compiled 21 times with -DQLA= -DQLB= -DQLC= -DQLD=
+// (build.py), so the classes build in parallel.
+#include "digest.cuh"
+
+#define QBX_CAT2(a, b, c, d) qbx_ops_##a##b##c##d
+#define QBX_CAT(a, b, c, d) QBX_CAT2(a, b, c, d)
+
+static int launch_eri(const ClassArgs &a, cudaStream_t s)
+{
+    if (a.ntasks <= 0) return QBX_OK;
+    eri_class_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+static int launch_digest(const DigestArgs &a, cudaStream_t s)
+{
+    if (a.ntasks <= 0) return QBX_OK;
+    digest_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
+{
+    if (a.ntasks <= 0) return QBX_OK;
+    scatter_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+
+extern const ClassOps QBX_CAT(QLA, QLB, QLC, QLD);
+const ClassOps QBX_CAT(QLA, QLB, QLC, QLD) = {QLA, QLB, QLC, QLD,
+                                              EriClass<QLA, QLB, QLC, QLD>::NCOMP,
+                                              launch_eri, launch_digest, launch_scatter};

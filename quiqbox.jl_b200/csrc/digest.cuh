@@ -1,0 +1,147 @@
+// Consumers of packed shell-quartet blocks: J/K digestion (= getGcore,
+// src/HartreeFock.jl:305-319) and the dense-tensor scatter (= the 8 permutational stores of
+// getOrbVectorIntegralCore!, src/Integration/Framework.jl:659-665).
+//
+// getGcore sums over all ordered index quartets,
+//     G[mu,nu] = sum DJ[sg,lm] (mu nu|lm sg) - sum DK[lm,sg] (mu lm|sg nu).
+// A unique shell quartet (AB|CD) (A >= B, C >= D, AB >= CD) stands for 8 ordered images; with
+// the block factor f = (A==B ? 1/2 : 1)(C==D ? 1/2 : 1)(AB==CD ? 1/2 : 1) and symmetric
+// densities every value v = (ab|cd) of the block contributes 6 updates to the half
+// accumulators
+//     Jt[a,b] += 2 f DJ[c,d] v     Jt[c,d] += 2 f DJ[a,b] v
+//     Kt[a,d] += f DK[b,c] v   Kt[b,d] += f DK[a,c] v   Kt[a,c] += f DK[b,d] v   Kt[b,c] += f DK[a,d] v
+// and G = (Jt + Jt^T) - (Kt + Kt^T) (k_finish_G in engine.cu).  One thread owns one quartet,
+// reduces its block into per-thread partial sums first and only then issues atomics, so a
+// block of n_a n_b n_c n_d values costs n_a n_b + n_c n_d + (n_a + n_b)(n_c + n_d) atomics.
+#pragma once
+#include "engine.h"
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
+{
+    constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD);
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= p.ntasks) return;
+    const int2 t = p.tasks[q];
+    const int2 sb = p.bra_shells[t.x], sk = p.ket_shells[t.y];
+    double f = 1.0;
+    if (sb.x == sb.y) f *= 0.5;
+    if (sk.x == sk.y) f *= 0.5;
+    if (p.same_class && t.x == t.y) f *= 0.5;
+    int fa[NA], fb[NB], fc[NCc], fd[ND];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) fa[i] = p.shell_bf[6 * sb.x + i];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) fb[i] = p.shell_bf[6 * sb.y + i];
+#pragma unroll
+    for (int i = 0; i < NCc; ++i) fc[i] = p.shell_bf[6 * sk.x + i];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) fd[i] = p.shell_bf[6 * sk.y + i];
+    const int64_t N = p.nbf, N2 = N * N;
+    const double *vq = p.vals + q;
+
+    // Coulomb part
+    double jcd[NCc * ND];
+#pragma unroll
+    for (int i = 0; i < NCc * ND; ++i) jcd[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (fa[a] < 0 || fb[b] < 0) continue;
+            const double dab = p.DJ[fa[a] + N * fb[b]];
+            double jab = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCc; ++c)
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    if (fc[c] < 0 || fd[d] < 0) continue;
+                    const double v = vq[(int64_t)(((a * NB + b) * NCc + c) * ND + d) * p.ntasks];
+                    jab = fma(p.DJ[fc[c] + N * fd[d]], v, jab);
+                    jcd[c * ND + d] = fma(dab, v, jcd[c * ND + d]);
+                }
+            atomicAdd(p.Jt + fa[a] + N * fb[b], 2.0 * f * jab);
+        }
+#pragma unroll
+    for (int c = 0; c < NCc; ++c)
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (fc[c] >= 0 && fd[d] >= 0) atomicAdd(p.Jt + fc[c] + N * fd[d], 2.0 * f * jcd[c * ND + d]);
+
+    // exchange part, one density at a time
+    for (int m = 0; m < p.nmat; ++m) {
+        const double *DK = p.DK + m * N2;
+        double *Kt = p.Kt + m * N2;
+        double kac[NA * NCc], kad[NA * ND], kbc[NB * NCc], kbd[NB * ND];
+#pragma unroll
+        for (int i = 0; i < NA * NCc; ++i) kac[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NA * ND; ++i) kad[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB * NCc; ++i) kbc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB * ND; ++i) kbd[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                if (fa[a] < 0 || fb[b] < 0) continue;
+#pragma unroll
+                for (int c = 0; c < NCc; ++c)
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        if (fc[c] < 0 || fd[d] < 0) continue;
+                        const double v = vq[(int64_t)(((a * NB + b) * NCc + c) * ND + d) * p.ntasks];
+                        kac[a * NCc + c] = fma(DK[fb[b] + N * fd[d]], v, kac[a * NCc + c]);
+                        kad[a * ND + d] = fma(DK[fb[b] + N * fc[c]], v, kad[a * ND + d]);
+                        kbc[b * NCc + c] = fma(DK[fa[a] + N * fd[d]], v, kbc[b * NCc + c]);
+                        kbd[b * ND + d] = fma(DK[fa[a] + N * fc[c]], v, kbd[b * ND + d]);
+                    }
+            }
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int c = 0; c < NCc; ++c)
+                if (fa[a] >= 0 && fc[c] >= 0) atomicAdd(Kt + fa[a] + N * fc[c], f * kac[a * NCc + c]);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (fa[a] >= 0 && fd[d] >= 0) atomicAdd(Kt + fa[a] + N * fd[d], f * kad[a * ND + d]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int c = 0; c < NCc; ++c)
+                if (fb[b] >= 0 && fc[c] >= 0) atomicAdd(Kt + fb[b] + N * fc[c], f * kbc[b * NCc + c]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (fb[b] >= 0 && fd[d] >= 0) atomicAdd(Kt + fb[b] + N * fd[d], f * kbd[b * ND + d]);
+    }
+}
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(128) scatter_kernel(ScatterArgs p)
+{
+    constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD);
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= p.ntasks) return;
+    const int2 t = p.tasks[q];
+    const int2 sb = p.bra_shells[t.x], sk = p.ket_shells[t.y];
+    const int64_t N = p.nbf;
+    double *T = p.tensor;
+    for (int a = 0; a < NA; ++a)
+        for (int b = 0; b < NB; ++b)
+            for (int c = 0; c < NCc; ++c)
+                for (int d = 0; d < ND; ++d) {
+                    const int64_t i = p.shell_bf[6 * sb.x + a], j = p.shell_bf[6 * sb.y + b];
+                    const int64_t k = p.shell_bf[6 * sk.x + c], l = p.shell_bf[6 * sk.y + d];
+                    if (i < 0 || j < 0 || k < 0 || l < 0) continue;
+                    const double v = p.vals[(int64_t)(((a * NB + b) * NCc + c) * ND + d) * p.ntasks + q];
+#define AT(w, x, y, z) T[(w) + N * ((x) + N * ((y) + N * (z)))]
+                    AT(i, j, k, l) = v; AT(j, i, k, l) = v; AT(i, j, l, k) = v; AT(j, i, l, k) = v;
+                    AT(k, l, i, j) = v; AT(k, l, j, i) = v; AT(l, k, i, j) = v; AT(l, k, j, i) = v;
+#undef AT
+                }
+}

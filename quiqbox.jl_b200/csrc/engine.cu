@@ -1,0 +1,658 @@
+// Host orchestration of the shell-quartet path (see engine.h).
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <numeric>
+#include <random>
+
+// ------------------------------------------------------------------ class registry
+#define QBX_DECL(a, b, c, d) extern const ClassOps qbx_ops_##a##b##c##d;
+#define QBX_FOR_ALL_CLASSES(X)                                                                                  \
+    X(0, 0, 0, 0)                                                                                               \
+    X(1, 0, 0, 0) X(1, 0, 1, 0)                                                                                 \
+    X(1, 1, 0, 0) X(1, 1, 1, 0) X(1, 1, 1, 1)                                                                   \
+    X(2, 0, 0, 0) X(2, 0, 1, 0) X(2, 0, 1, 1) X(2, 0, 2, 0)                                                     \
+    X(2, 1, 0, 0) X(2, 1, 1, 0) X(2, 1, 1, 1) X(2, 1, 2, 0) X(2, 1, 2, 1)                                       \
+    X(2, 2, 0, 0) X(2, 2, 1, 0) X(2, 2, 1, 1) X(2, 2, 2, 0) X(2, 2, 2, 1) X(2, 2, 2, 2)
+QBX_FOR_ALL_CLASSES(QBX_DECL)
+
+static inline int pair_cls(int la, int lb) { return la * (la + 1) / 2 + lb; }
+
+const ClassOps *qbx_class_ops(int bc, int kc)
+{
+    static const ClassOps *tab[QBX_NPAIRCLS][QBX_NPAIRCLS] = {{nullptr}};
+    static bool init = false;
+    if (!init) {
+#define QBX_REG(a, b, c, d) tab[pair_cls(a, b)][pair_cls(c, d)] = &qbx_ops_##a##b##c##d;
+        QBX_FOR_ALL_CLASSES(QBX_REG)
+        init = true;
+    }
+    return (bc >= 0 && bc < QBX_NPAIRCLS && kc >= 0 && kc <= bc) ? tab[bc][kc] : nullptr;
+}
+
+static const int kClsLa[QBX_NPAIRCLS] = {0, 1, 1, 2, 2, 2};
+static const int kClsLb[QBX_NPAIRCLS] = {0, 0, 1, 0, 1, 2};
+
+// ------------------------------------------------------------------ flop model
+static void comps_of(int l, int (*c)[3])
+{
+    int n = 0;
+    for (int i = l; i >= 0; --i)
+        for (int j = l - i; j >= 0; --j) { c[n][0] = i; c[n][1] = j; c[n][2] = l - i - j; ++n; }
+}
+
+double qbx_model_flops_prim(int la, int lb, int lc, int ld)
+{
+    const int L = la + lb + lc + ld, E = la + lb, F = lc + ld;
+    double vrr = 0;
+    int ce[45][3], cf[45][3];
+    for (int e = 0; e <= E; ++e)
+        for (int f = 0; f <= F; ++f) {
+            if (e == 0 && f == 0) continue;
+            comps_of(e, ce); comps_of(f, cf);
+            for (int m = 0; m <= L - e - f; ++m)
+                for (int a = 0; a < qbx_nc(e); ++a)
+                    for (int b = 0; b < qbx_nc(f); ++b) {
+                        int ax, low;
+                        if (f > 0) { ax = cf[b][0] > 0 ? 0 : (cf[b][1] > 0 ? 1 : 2); low = cf[b][ax]; }
+                        else { ax = ce[a][0] > 0 ? 0 : (ce[a][1] > 0 ? 1 : 2); low = ce[a][ax]; }
+                        double c = 3;
+                        if (low > 1) c += 4;
+                        if (f > 0 && ce[a][ax] > 0) c += 2;
+                        vrr += c;
+                    }
+        }
+    double se = 0, sf = 0;
+    for (int e = la; e <= E; ++e) se += qbx_nc(e);
+    for (int f = lc; f <= F; ++f) sf += qbx_nc(f);
+    return 84.0 + 25.0 + 3.0 * L + vrr + 2.0 * se * sf;
+}
+
+double qbx_model_flops_hrr(int la, int lb, int lc, int ld)
+{
+    const int E = la + lb, F = lc + ld;
+    double sf = 0, h = 0;
+    for (int f = lc; f <= F; ++f) sf += qbx_nc(f);
+    for (int b = 1; b <= lb; ++b)
+        for (int a = la; a <= E - b; ++a) h += 2.0 * qbx_nc(a) * qbx_nc(b) * sf;
+    for (int d = 1; d <= ld; ++d)
+        for (int c = lc; c <= F - d; ++c) h += 2.0 * qbx_nc(c) * qbx_nc(d) * qbx_nc(la) * qbx_nc(lb);
+    return h;
+}
+
+// ------------------------------------------------------------------ small kernels
+namespace {
+
+__global__ void k_diag_tasks(int n, int2 *t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = make_int2(i, i);
+}
+
+// Q[i] = sqrt(max_ab |(ab|ab)|) over the components of pair i
+__global__ void k_schwarz(const double *vals, int n, int nab, double *Q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double m = 0.0;
+    for (int ab = 0; ab < nab; ++ab) m = fmax(m, fabs(vals[(int64_t)(ab * nab + ab) * n + i]));
+    Q[i] = sqrt(m);
+}
+
+__global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol, int *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int jmax = same ? i + 1 : nk;
+    const double qi = Qb[i];
+    int c = 0;
+    for (int j = 0; j < jmax; ++j) c += (qi * Qk[j] >= tol);
+    cnt[i] = c;
+}
+
+#define QBX_TASK_CHUNK 4096
+// one warp per bra row: compact the surviving kets in order; keep the chunks of this rank
+__global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol,
+                             const int64_t *rowoff, int rank, int nranks, int2 *tasks)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+    if (i >= nb) return;
+    const int jmax = same ? i + 1 : nk;
+    const double qi = Qb[i];
+    int64_t g = rowoff[i];
+    for (int j0 = 0; j0 < jmax; j0 += 32) {
+        const int j = j0 + lane;
+        const bool pass = j < jmax && qi * Qk[j] >= tol;
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            const int64_t gg = g + __popc(mask & ((1u << lane) - 1u));
+            const int64_t c = gg / QBX_TASK_CHUNK;
+            if (c % nranks == rank) tasks[(c / nranks) * QBX_TASK_CHUNK + gg % QBX_TASK_CHUNK] = make_int2(i, j);
+        }
+        g += __popc(mask);
+    }
+}
+
+__global__ void k_task_cost(const int2 *tasks, int64_t n, const int *poffb, const int *poffk, double *sum)
+{
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int2 t = tasks[q];
+        acc += (double)(poffb[t.x + 1] - poffb[t.x]) * (double)(poffk[t.y + 1] - poffk[t.y]);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(sum, red[0]);
+}
+
+__global__ void k_finish_G(int64_t N, int nmat, const double *Jt, const double *Kt, double *G)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= N * N) return;
+    const int64_t i = e % N, j = e / N, et = j + N * i;
+    const double jv = Jt[e] + Jt[et];
+    for (int m = 0; m < nmat; ++m) G[m * N * N + e] = jv - (Kt[m * N * N + e] + Kt[m * N * N + et]);
+}
+
+__global__ void k_sum(const double *v, int64_t n, double *sum)
+{
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) acc += v[q];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(sum, red[0]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ shell reconstruction
+static int comp_index(const int32_t *a) { return CIDX(a[1], a[2]); }
+
+Engine *Engine::create(int64_t nprim, const double *cen, const double *xpn, const int32_t *ang, int64_t nbf,
+                       const int64_t *bf_off, const int64_t *bf_prim, const double *bf_w)
+{
+    (void)nprim;
+    std::vector<HostShell> shells;
+    struct Key {
+        double c[3]; int l; std::vector<double> x;
+        bool operator<(const Key &o) const {
+            if (l != o.l) return l < o.l;
+            for (int d = 0; d < 3; ++d) if (c[d] != o.c[d]) return c[d] < o.c[d];
+            return x < o.x;
+        }
+    };
+    std::map<Key, std::vector<int>> open;
+    for (int64_t f = 0; f < nbf; ++f) {
+        const int64_t p0 = bf_off[f], p1 = bf_off[f + 1];
+        const int64_t q0 = bf_prim[p0];
+        Key k;
+        for (int d = 0; d < 3; ++d) k.c[d] = cen[3 * q0 + d];
+        k.l = ang[3 * q0] + ang[3 * q0 + 1] + ang[3 * q0 + 2];
+        if (k.l > QBX_MAX_L) return nullptr;
+        for (int64_t p = p0; p < p1; ++p) {
+            const int64_t q = bf_prim[p];
+            for (int d = 0; d < 3; ++d)
+                if (cen[3 * q + d] != k.c[d] || ang[3 * q + d] != ang[3 * q0 + d]) return nullptr;   // not a shell function
+            k.x.push_back(xpn[q]);
+        }
+        const int comp = comp_index(ang + 3 * q0);
+        int found = -1;
+        double ratio = 1.0;
+        for (int si : open[k]) {
+            HostShell &s = shells[si];
+            if (s.bf[comp] >= 0) continue;
+            bool ok = true, have = false;
+            double r = 0.0;
+            for (size_t p = 0; p < k.x.size() && ok; ++p) {
+                const double w = bf_w[p0 + p], c = s.coef[p];
+                if (c == 0.0) { ok = (w == 0.0); continue; }
+                const double rp = w / c;
+                if (!have) { r = rp; have = true; }
+                else ok = fabs(rp - r) <= 1e-12 * fabs(r);
+            }
+            if (ok && have) { found = si; ratio = r; break; }
+        }
+        if (found < 0) {
+            HostShell s;
+            s.l = k.l;
+            for (int d = 0; d < 3; ++d) s.cen[d] = k.c[d];
+            s.xpn = k.x;
+            s.coef.assign(bf_w + p0, bf_w + p1);
+            shells.push_back(s);
+            found = (int)shells.size() - 1;
+            open[k].push_back(found);
+            ratio = 1.0;
+        }
+        shells[found].bf[comp] = (int)f;
+        shells[found].scale[comp] = ratio;
+    }
+    std::stable_sort(shells.begin(), shells.end(), [](const HostShell &a, const HostShell &b) { return a.l < b.l; });
+    return from_shells(shells, nbf, false);
+}
+
+Engine *Engine::from_shells(const std::vector<HostShell> &shells, int64_t nbf, bool pair_adjacent)
+{
+    Engine *e = new Engine;
+    e->shells_ = shells;
+    e->nbf_ = nbf;
+    for (auto &s : shells) e->maxl_ = std::max(e->maxl_, s.l);
+    if (e->upload(pair_adjacent) != QBX_OK) { delete e; return nullptr; }
+    return e;
+}
+
+static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::vector<std::pair<int, int>> sp,
+                         bool sort_by_nprim, DevPairSet &out)
+{
+    struct Rec { double v[8]; };
+    std::vector<std::vector<Rec>> prims(sp.size());
+    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
+    for (size_t i = 0; i < sp.size(); ++i) {
+        const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
+        double ab2 = 0;
+        for (int d = 0; d < 3; ++d) ab2 += (A.cen[d] - B.cen[d]) * (A.cen[d] - B.cen[d]);
+        for (size_t pa = 0; pa < A.xpn.size(); ++pa)
+            for (size_t pb = 0; pb < B.xpn.size(); ++pb) {
+                const double a = A.xpn[pa], b = B.xpn[pb], z = a + b;
+                const double K = pref * A.coef[pa] * B.coef[pb] * exp(-a * b / z * ab2) / z;
+                if (fabs(K) < 1e-24) continue;
+                Rec r;
+                r.v[0] = z;
+                for (int d = 0; d < 3; ++d) r.v[1 + d] = (a * A.cen[d] + b * B.cen[d]) / z;
+                r.v[4] = K; r.v[5] = b; r.v[6] = 0.5 / z; r.v[7] = 1.0 / z;
+                prims[i].push_back(r);
+            }
+    }
+    std::vector<int> order(sp.size());
+    std::iota(order.begin(), order.end(), 0);
+    if (sort_by_nprim)
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prims[x].size() > prims[y].size(); });
+    std::vector<int2> shells(sp.size());
+    std::vector<int> poff(sp.size() + 1, 0);
+    std::vector<double> geom(8 * sp.size(), 0.0), prim;
+    out.h_nprim.resize(sp.size());
+    for (size_t n = 0; n < sp.size(); ++n) {
+        const int i = order[n];
+        const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
+        shells[n] = make_int2(sp[i].first, sp[i].second);
+        for (int d = 0; d < 3; ++d) { geom[8 * n + d] = A.cen[d]; geom[8 * n + 3 + d] = A.cen[d] - B.cen[d]; }
+        for (auto &r : prims[i]) prim.insert(prim.end(), r.v, r.v + 8);
+        poff[n + 1] = poff[n] + (int)prims[i].size();
+        out.h_nprim[n] = (int)prims[i].size();
+    }
+    out.la = la; out.lb = lb; out.npair = (int)sp.size(); out.nprim = poff.back();
+    QBX_CUDA(cudaMalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
+    QBX_CUDA(cudaMalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&out.geom, std::max<size_t>(1, geom.size()) * sizeof(double)));
+    QBX_CUDA(cudaMalloc(&out.prim, std::max<size_t>(1, prim.size()) * sizeof(double)));
+    QBX_CUDA(cudaMalloc(&out.schwarz, std::max<size_t>(1, sp.size()) * sizeof(double)));
+    if (!sp.empty()) {
+        QBX_CUDA(cudaMemcpy(out.shells, shells.data(), shells.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        QBX_CUDA(cudaMemcpy(out.geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    QBX_CUDA(cudaMemcpy(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!prim.empty()) QBX_CUDA(cudaMemcpy(out.prim, prim.data(), prim.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return QBX_OK;
+}
+
+int Engine::upload(bool pair_adjacent)
+{
+    const size_t ns = shells_.size();
+    std::vector<int> bf(6 * ns);
+    std::vector<double> sc(6 * ns);
+    for (size_t s = 0; s < ns; ++s)
+        for (int c = 0; c < 6; ++c) { bf[6 * s + c] = shells_[s].bf[c]; sc[6 * s + c] = shells_[s].scale[c]; }
+    QBX_CUDA(cudaMalloc(&d_shell_bf_, std::max<size_t>(1, bf.size()) * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&d_shell_scale_, std::max<size_t>(1, sc.size()) * sizeof(double)));
+    QBX_CUDA(cudaMemcpy(d_shell_bf_, bf.data(), bf.size() * sizeof(int), cudaMemcpyHostToDevice));
+    QBX_CUDA(cudaMemcpy(d_shell_scale_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<std::pair<int, int>> sp[QBX_NPAIRCLS];
+    if (pair_adjacent) {
+        for (size_t s = 0; s + 1 < ns; s += 2) {
+            int a = (int)s, b = (int)s + 1;
+            if (shells_[a].l < shells_[b].l) std::swap(a, b);
+            sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({a, b});
+        }
+    } else {
+        for (size_t a = 0; a < ns; ++a)           // shells are sorted by l, so a >= b implies la >= lb
+            for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
+    }
+    for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc]);
+        if (rc) return rc;
+    }
+    QBX_CUDA(cudaEventCreate(&ev0_));
+    QBX_CUDA(cudaEventCreate(&ev1_));
+    return QBX_OK;
+}
+
+Engine::~Engine()
+{
+    release_store();
+    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); }
+    cudaFree(d_shell_bf_); cudaFree(d_shell_scale_);
+    cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+}
+
+void Engine::release_store()
+{
+    for (int b = 0; b < QBX_NPAIRCLS; ++b)
+        for (int k = 0; k < QBX_NPAIRCLS; ++k) {
+            cudaFree(tasks_[b][k].tasks); tasks_[b][k] = TaskList();
+            cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
+        }
+    mode_ = -1;
+    n_quartets_ = n_values_ = stored_bytes_ = 0;
+    n_primq_ = model_flops_ = 0;
+}
+
+void Engine::info(int64_t *info) const
+{
+    info[1] = (int64_t)shells_.size();
+    info[2] = maxl_;
+    info[3] = 1;
+    int64_t np = 0;
+    for (auto &p : pairs_) np += p.npair;
+    info[4] = np;
+    info[5] = n_quartets_;
+    info[6] = n_values_;
+    info[7] = stored_bytes_;
+    info[8] = (int64_t)n_primq_;
+    info[9] = (int64_t)model_flops_;
+}
+
+// ------------------------------------------------------------------ ERI launches
+int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s)
+{
+    const ClassOps *ops = qbx_class_ops(bc, kc);
+    if (!ops) { qbx_set_error("internal: no kernel for this class"); return QBX_ERR_STATE; }
+    ClassArgs a;
+    a.bra = pairs_[bc].view(); a.ket = pairs_[kc].view();
+    a.tasks = tasks; a.ntasks = n; a.out = out;
+    a.shell_scale = d_shell_scale_;
+    a.boys = qbx_boys_table();
+    return ops->eri(a, s);
+}
+
+int Engine::ensure_schwarz(cudaStream_t s)
+{
+    if (have_schwarz_) return QBX_OK;
+    for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+        DevPairSet &P = pairs_[pc];
+        if (P.npair == 0) continue;
+        const ClassOps *ops = qbx_class_ops(pc, pc);
+        int2 *t = nullptr; double *v = nullptr;
+        QBX_CUDA(cudaMalloc(&t, P.npair * sizeof(int2)));
+        QBX_CUDA(cudaMalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
+        k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, s>>>(P.npair, t);
+        int rc = run_eri(pc, pc, t, P.npair, v, s);
+        if (rc) return rc;
+        const int nab = qbx_nc(P.la) * qbx_nc(P.lb);
+        k_schwarz<<<(P.npair + 127) / 128, 128, 0, s>>>(v, P.npair, nab, P.schwarz);
+        QBX_CUDA(cudaGetLastError());
+        QBX_CUDA(cudaStreamSynchronize(s));
+        cudaFree(t); cudaFree(v);
+    }
+    have_schwarz_ = true;
+    return QBX_OK;
+}
+
+int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s)
+{
+    out = TaskList();
+    const DevPairSet &B = pairs_[bc], &K = pairs_[kc];
+    if (B.npair == 0 || K.npair == 0) return QBX_OK;
+    const int same = (bc == kc);
+    int *d_cnt = nullptr;
+    QBX_CUDA(cudaMalloc(&d_cnt, B.npair * sizeof(int)));
+    k_count_tasks<<<(B.npair + 127) / 128, 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol, d_cnt);
+    std::vector<int> cnt(B.npair);
+    QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, B.npair * sizeof(int), cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_cnt);
+    std::vector<int64_t> rowoff(B.npair + 1, 0);
+    for (int i = 0; i < B.npair; ++i) rowoff[i + 1] = rowoff[i] + cnt[i];
+    const int64_t total = rowoff.back();
+    const int64_t nfull = total / QBX_TASK_CHUNK, rem = total % QBX_TASK_CHUNK;
+    int64_t mine = 0;
+    for (int64_t c = rank; c < nfull; c += nranks) mine += QBX_TASK_CHUNK;
+    if (rem && nfull % nranks == rank) mine += rem;
+    out.n = mine;
+    if (mine == 0) return QBX_OK;
+    int64_t *d_off = nullptr;
+    QBX_CUDA(cudaMalloc(&d_off, rowoff.size() * sizeof(int64_t)));
+    QBX_CUDA(cudaMemcpyAsync(d_off, rowoff.data(), rowoff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    QBX_CUDA(cudaMalloc(&out.tasks, mine * sizeof(int2)));
+    const int64_t threads = (int64_t)B.npair * 32;
+    k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol,
+                                                                   d_off, rank, nranks, out.tasks);
+    QBX_CUDA(cudaGetLastError());
+    double *d_sum = nullptr;
+    QBX_CUDA(cudaMalloc(&d_sum, sizeof(double)));
+    QBX_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), s));
+    k_task_cost<<<296, 256, 0, s>>>(out.tasks, mine, B.prim_off, K.prim_off, d_sum);
+    QBX_CUDA(cudaMemcpyAsync(&out.nprimq, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_off); cudaFree(d_sum);
+    return QBX_OK;
+}
+
+static const int64_t kChunkDoubles = 8ll << 20;      // 64 MiB staging block: stays in the 126 MB L2
+
+int Engine::fill_tensor(double *d_tensor, cudaStream_t s, double *stats)
+{
+    int rc = ensure_schwarz(s);
+    if (rc) return rc;
+    if (!chunk_) { QBX_CUDA(cudaMalloc(&chunk_, kChunkDoubles * sizeof(double))); chunk_doubles_ = kChunkDoubles; }
+    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+        for (int kc = 0; kc <= bc; ++kc) {
+            TaskList tl;
+            if ((rc = build_tasks(bc, kc, 0.0, 0, 1, tl, s))) return rc;
+            if (tl.n == 0) continue;
+            const ClassOps *ops = qbx_class_ops(bc, kc);
+            const int64_t step = std::max<int64_t>(128, (chunk_doubles_ / ops->ncomp) / 128 * 128);
+            for (int64_t o = 0; o < tl.n; o += step) {
+                const int64_t n = std::min(step, tl.n - o);
+                if ((rc = run_eri(bc, kc, tl.tasks + o, n, chunk_, s))) return rc;
+                ScatterArgs a{pairs_[bc].shells, pairs_[kc].shells, tl.tasks + o, n, chunk_, d_shell_bf_, nbf_, d_tensor};
+                if ((rc = ops->scatter(a, s))) return rc;
+                stats[0] += 2;
+            }
+            stats[3] += tl.nprimq;
+            QBX_CUDA(cudaStreamSynchronize(s));
+            cudaFree(tl.tasks);
+        }
+    return QBX_OK;
+}
+
+int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, double *stats)
+{
+    release_store();
+    int rc = ensure_schwarz(s);
+    if (rc) return rc;
+    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+        for (int kc = 0; kc <= bc; ++kc) {
+            if ((rc = build_tasks(bc, kc, tol, rank, nranks, tasks_[bc][kc], s))) return rc;
+            const ClassOps *ops = qbx_class_ops(bc, kc);
+            const TaskList &tl = tasks_[bc][kc];
+            n_quartets_ += tl.n;
+            n_values_ += tl.n * ops->ncomp;
+            n_primq_ += tl.nprimq;
+            model_flops_ += tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
+                            (double)tl.n * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
+            if (mode == 0 && tl.n > 0) {
+                const size_t bytes = (size_t)tl.n * ops->ncomp * sizeof(double);
+                if (cudaMalloc(&vals_[bc][kc], bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    qbx_set_error("qbx_eri_store: packed ERI store does not fit in device memory; use mode 1 (direct)");
+                    release_store();
+                    return QBX_ERR_NOMEM;
+                }
+                stored_bytes_ += (int64_t)bytes;
+            }
+        }
+    if (!d_Jt_) {
+        QBX_CUDA(cudaMalloc(&d_Jt_, nbf_ * nbf_ * sizeof(double)));
+        QBX_CUDA(cudaMalloc(&d_Kt_, 2 * nbf_ * nbf_ * sizeof(double)));
+    }
+    mode_ = mode;
+    if (mode == 0) {
+        if ((rc = recompute(s, stats))) return rc;
+    } else if (!chunk_) {
+        QBX_CUDA(cudaMalloc(&chunk_, kChunkDoubles * sizeof(double)));
+        chunk_doubles_ = kChunkDoubles;
+    }
+    QBX_CUDA(cudaStreamSynchronize(s));
+    return QBX_OK;
+}
+
+int Engine::recompute(cudaStream_t s, double *stats)
+{
+    if (mode_ != 0) { qbx_set_error("recompute: stored mode only"); return QBX_ERR_STATE; }
+    QBX_CUDA(cudaEventRecord(ev0_, s));
+    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+        for (int kc = 0; kc <= bc; ++kc) {
+            const TaskList &tl = tasks_[bc][kc];
+            if (tl.n == 0) continue;
+            int rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], s);
+            if (rc) return rc;
+            stats[0] += 1;
+        }
+    QBX_CUDA(cudaEventRecord(ev1_, s));
+    QBX_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0;
+    QBX_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats[1] += ms * 1e-3;
+    stats[3] += n_primq_;
+    stats[4] += model_flops_;
+    return QBX_OK;
+}
+
+int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats)
+{
+    if (mode_ != 0 && mode_ != 1) { qbx_set_error("fock: no ERI representation stored"); return QBX_ERR_STATE; }
+    const int64_t N2 = nbf_ * nbf_;
+    QBX_CUDA(cudaMemsetAsync(d_Jt_, 0, N2 * sizeof(double), s));
+    QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * N2 * sizeof(double), s));
+    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+        for (int kc = 0; kc <= bc; ++kc) {
+            const TaskList &tl = tasks_[bc][kc];
+            if (tl.n == 0) continue;
+            const ClassOps *ops = qbx_class_ops(bc, kc);
+            DigestArgs a;
+            a.bra_shells = pairs_[bc].shells; a.ket_shells = pairs_[kc].shells;
+            a.shell_bf = d_shell_bf_; a.nbf = (int)nbf_; a.nmat = nmat; a.same_class = (bc == kc);
+            a.DJ = dDJ; a.DK = dDK; a.Jt = d_Jt_; a.Kt = d_Kt_;
+            if (mode_ == 0) {
+                a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
+                int rc = ops->digest(a, s);
+                if (rc) return rc;
+                stats[0] += 1;
+                stats[5] += (double)tl.n * ops->ncomp * sizeof(double);
+            } else {
+                const int64_t step = std::max<int64_t>(128, (chunk_doubles_ / ops->ncomp) / 128 * 128);
+                for (int64_t o = 0; o < tl.n; o += step) {
+                    const int64_t n = std::min(step, tl.n - o);
+                    int rc = run_eri(bc, kc, tl.tasks + o, n, chunk_, s);
+                    if (rc) return rc;
+                    a.tasks = tl.tasks + o; a.ntasks = n; a.vals = chunk_;
+                    if ((rc = ops->digest(a, s))) return rc;
+                    stats[0] += 2;
+                }
+                stats[3] += tl.nprimq;
+            }
+        }
+    if (mode_ == 1) stats[4] += model_flops_;
+    k_finish_G<<<(unsigned)((N2 + 255) / 256), 256, 0, s>>>(nbf_, nmat, d_Jt_, d_Kt_, dG);
+    QBX_CUDA(cudaGetLastError());
+    stats[0] += 1;
+    return QBX_OK;
+}
+
+// ------------------------------------------------------------------ synthetic class batches
+int Engine::synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_t seed, double *secs, double *checksum,
+                      int64_t nsample, double *sample_out, double *sample_geom, cudaStream_t s)
+{
+    if (pair_cls(la, lb) < pair_cls(lc, ld)) { std::swap(la, lc); std::swap(lb, ld); }
+    const int bc = pair_cls(la, lb), kc = pair_cls(lc, ld);
+    const int64_t np = (int64_t)ceil(sqrt((double)nq));
+    // splitmix64: centres uniform in a 10-bohr cube, exponents log-uniform in
+    // [0.1, 1e3], coefficients uniform in [-1, 1]
+    uint64_t st = seed ^ ((uint64_t)(la * 27 + lb * 9 + lc * 3 + ld) << 32) ^ ((uint64_t)K << 48) ^ 20261017ull;
+    auto next = [&]() {
+        uint64_t z = (st += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return (double)((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0);
+    };
+    std::vector<HostShell> sh;
+    auto add = [&](int l) {
+        HostShell h;
+        h.l = l;
+        for (int d = 0; d < 3; ++d) h.cen[d] = 10.0 * next();
+        for (int k = 0; k < K; ++k) { h.xpn.push_back(0.1 * pow(1e4, next())); h.coef.push_back(2.0 * next() - 1.0); }
+        sh.push_back(h);
+    };
+    for (int64_t i = 0; i < np; ++i) { add(la); add(lb); }
+    for (int64_t i = 0; i < np; ++i) { add(lc); add(ld); }
+    // bra pairs come first, ket pairs second; when the pair classes coincide they share one set
+    Engine *e = from_shells(sh, 0, true);
+    if (!e) return QBX_ERR_CUDA;
+    const ClassOps *ops = qbx_class_ops(bc, kc);
+    // pair indices: adjacent pairs were appended in order, so within a class the first np are
+    // the bra pairs and (if bc == kc) the next np the ket pairs
+    const int koff = (bc == kc) ? (int)np : 0;
+    std::vector<int2> tasks((size_t)nq);
+    for (int64_t q = 0; q < nq; ++q) tasks[q] = make_int2((int)(q / np), koff + (int)(q % np));
+    int2 *d_t = nullptr; double *d_v = nullptr, *d_sum = nullptr;
+    int rc = QBX_OK;
+    do {
+        if (cudaMalloc(&d_t, nq * sizeof(int2)) != cudaSuccess || cudaMalloc(&d_v, (size_t)nq * ops->ncomp * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&d_sum, sizeof(double)) != cudaSuccess) { qbx_set_error("qbx_prim_batch: out of device memory"); rc = QBX_ERR_NOMEM; break; }
+        cudaMemcpyAsync(d_t, tasks.data(), nq * sizeof(int2), cudaMemcpyHostToDevice, s);
+        if ((rc = e->run_eri(bc, kc, d_t, nq, d_v, s))) break;           // warm-up
+        cudaEventRecord(e->ev0_, s);
+        if ((rc = e->run_eri(bc, kc, d_t, nq, d_v, s))) break;
+        cudaEventRecord(e->ev1_, s);
+        cudaMemsetAsync(d_sum, 0, sizeof(double), s);
+        k_sum<<<296, 256, 0, s>>>(d_v, nq * ops->ncomp, d_sum);
+        cudaMemcpyAsync(checksum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { qbx_set_error(std::string("qbx_prim_batch: ") + cudaGetErrorString(cudaGetLastError())); rc = QBX_ERR_CUDA; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev0_, e->ev1_);
+        *secs = ms * 1e-3;
+        const int64_t ns = std::min(nsample, nq);
+        if (ns > 0 && sample_out && sample_geom) {
+            std::vector<double> all((size_t)ops->ncomp);
+            for (int64_t q = 0; q < ns; ++q) {
+                cudaMemcpy2D(sample_out + q * ops->ncomp, sizeof(double), d_v + q, nq * sizeof(double), sizeof(double),
+                             ops->ncomp, cudaMemcpyDeviceToHost);
+                const int ids[4] = {2 * (int)(q / np), 2 * (int)(q / np) + 1, 2 * (int)(np + q % np), 2 * (int)(np + q % np) + 1};
+                double *g = sample_geom + q * 4 * (3 + 2 * K);
+                for (int t = 0; t < 4; ++t) {
+                    const HostShell &h = sh[ids[t]];
+                    for (int d = 0; d < 3; ++d) g[t * (3 + 2 * K) + d] = h.cen[d];
+                    for (int k = 0; k < K; ++k) { g[t * (3 + 2 * K) + 3 + k] = h.xpn[k]; g[t * (3 + 2 * K) + 3 + K + k] = h.coef[k]; }
+                }
+            }
+        }
+    } while (0);
+    cudaFree(d_t); cudaFree(d_v); cudaFree(d_sum);
+    delete e;
+    return rc;
+}

@@ -1,0 +1,108 @@
+// Shell-level host machinery of libqbx.so: shell reconstruction from the flat primitive
+// table, shell-pair data, Schwarz bounds, per-class shell-quartet task lists, the packed
+// ERI store and the Fock-build driver.  Device kernels live in eri_class.cuh / digest.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "eri_class.cuh"
+
+struct HostShell {
+    int l = 0;
+    double cen[3] = {0, 0, 0};
+    std::vector<double> xpn, coef;       // radial contraction (component-independent)
+    int bf[6] = {-1, -1, -1, -1, -1, -1}; // basis-function index per Cartesian component
+    double scale[6] = {1, 1, 1, 1, 1, 1}; // per-component weight factor
+};
+
+// arguments of the per-class consumers of a packed value block
+struct DigestArgs {
+    const int2 *bra_shells, *ket_shells;
+    const int2 *tasks;
+    int64_t ntasks;
+    const double *vals;          // [ncomp][ntasks]
+    const int *shell_bf;         // [nshell][6]
+    int nbf, nmat, same_class;
+    const double *DJ, *DK;       // nbf^2, nmat * nbf^2
+    double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
+};
+struct ScatterArgs {
+    const int2 *bra_shells, *ket_shells;
+    const int2 *tasks;
+    int64_t ntasks;
+    const double *vals;
+    const int *shell_bf;
+    int64_t nbf;
+    double *tensor;              // nbf^4, column-major
+};
+
+struct ClassOps {
+    int la, lb, lc, ld, ncomp;
+    int (*eri)(const ClassArgs &, cudaStream_t);
+    int (*digest)(const DigestArgs &, cudaStream_t);
+    int (*scatter)(const ScatterArgs &, cudaStream_t);
+};
+const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
+
+struct DevPairSet {
+    int la = 0, lb = 0, npair = 0, nprim = 0;
+    int2 *shells = nullptr;
+    int *prim_off = nullptr;
+    double *geom = nullptr, *prim = nullptr, *schwarz = nullptr;
+    std::vector<int> h_nprim;            // primitive pairs per pair (host copy, for cost models)
+    PairSet view() const { return PairSet{shells, prim_off, geom, prim, npair}; }
+};
+
+struct TaskList {
+    int2 *tasks = nullptr;
+    int64_t n = 0;
+    double nprimq = 0;                   // primitive quartets behind these tasks
+};
+
+class Engine {
+public:
+    static Engine *create(int64_t nprim, const double *cen, const double *xpn, const int32_t *ang, int64_t nbf,
+                          const int64_t *bf_off, const int64_t *bf_prim, const double *bf_w);
+    static Engine *from_shells(const std::vector<HostShell> &shells, int64_t nbf, bool pair_adjacent);
+    ~Engine();
+
+    void info(int64_t *info) const;
+    int fill_tensor(double *d_tensor, cudaStream_t s, double *stats);
+    int store(double tol, int mode, int rank, int nranks, cudaStream_t s, double *stats);
+    int recompute(cudaStream_t s, double *stats);
+    int fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats);
+    void release_store();
+
+    static int synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_t seed, double *secs,
+                         double *checksum, int64_t nsample, double *sample_out, double *sample_geom, cudaStream_t s);
+
+private:
+    Engine() = default;
+    int upload(bool pair_adjacent);
+    int ensure_schwarz(cudaStream_t s);
+    int build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s);
+    int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s);
+
+    std::vector<HostShell> shells_;
+    int64_t nbf_ = 0;
+    int maxl_ = 0;
+    int *d_shell_bf_ = nullptr;
+    double *d_shell_scale_ = nullptr;
+    DevPairSet pairs_[QBX_NPAIRCLS];
+    bool have_schwarz_ = false;
+    // stored state
+    int mode_ = -1;
+    TaskList tasks_[QBX_NPAIRCLS][QBX_NPAIRCLS];
+    double *vals_[QBX_NPAIRCLS][QBX_NPAIRCLS] = {{nullptr}};
+    double *chunk_ = nullptr;            // direct mode / tensor fill staging
+    int64_t chunk_doubles_ = 0;
+    double *d_Jt_ = nullptr, *d_Kt_ = nullptr;
+    int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
+    double n_primq_ = 0, model_flops_ = 0;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+};
+
+double qbx_model_flops_prim(int la, int lb, int lc, int ld);   // prim + acc of SURVEY.md 8(d)
+double qbx_model_flops_hrr(int la, int lb, int lc, int ld);

@@ -1,0 +1,49 @@
+// Internal declarations shared by the translation units of libqbx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/qbx.h"
+#include "boys.cuh"
+
+#define QBX_MAX_L 2                 // class kernels cover s, p, d
+#define QBX_NPAIRCLS 6              // (ss) (ps) (pp) (ds) (dp) (dd)
+#define QBX_NCLASS 21               // canonical quartet classes, bra pair class >= ket pair class
+#define QBX_GEN_MAXL 64             // generic kernel: max total angular momentum of a quartet
+#define QBX_GEN_MAXAX 32            // generic kernel: max angular momentum sum on one axis
+
+void qbx_set_error(const std::string &msg);
+#define QBX_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            qbx_set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " + \
+                          __FILE__ + ":" + std::to_string(__LINE__));                         \
+            return QBX_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+__host__ __device__ constexpr int qbx_nc(int l) { return (l + 1) * (l + 2) / 2; }
+
+// flat primitive table + CSR on the device (generic kernels)
+struct DevFlat {
+    int64_t nprim, nbf, nnz;
+    double *cen, *xpn;      // 3 x nprim, nprim
+    int32_t *ang;           // 3 x nprim
+    int64_t *bf_off, *bf_prim;
+    double *bf_w;
+};
+
+BoysTable qbx_boys_table();         // device pointers of the Taylor table (built on first use)
+cudaStream_t qbx_stream();
+
+// generic.cu
+int qbx_launch_generic_quartets(const DevFlat &f, int64_t n, const int64_t *d_ijkl, double *d_out, cudaStream_t s);
+int qbx_launch_generic_tensor(const DevFlat &f, double *d_tensor, cudaStream_t s);
+int qbx_launch_one_body(const DevFlat &f, int kind, int64_t nnuc, const double *dZ, const double *dR, double *d_out,
+                        cudaStream_t s);
+int qbx_launch_dense_gcore(int64_t n, const double *dH, int nmat, const double *dDJ, const double *dDK, double *dG,
+                           cudaStream_t s);
+int qbx_launch_boys(int64_t n, const double *dT, int mmax, int table, double *d_out, cudaStream_t s);

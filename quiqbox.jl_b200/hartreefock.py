@@ -251,3 +251,47 @@ def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFc
             break
         converged = True if (method, thr) == config.strategy.stages()[-1] else converged
     return Cs, Ds, Fs, eps, Etot, converged, step, nbuild[0], trace
+
+
+# ---------------------------------------------------------------------------- public entry
+def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=False, mode=None,
+                   screen_tol=1e-12, comm=None):
+    """runHartreeFock(nucInfo, bs[, config]) -> HFfinalInfo  (HartreeFock.jl:953-1046).
+
+    ``nucInfo`` is a NuclearCluster (or ``(nucSyms, nucCoords)``), ``bs`` a list of GTOs.  The
+    one-electron matrices and every Fock build run on the GPU through libqbx.so
+    (initializeHartreeFock :178-210 -> qbx_one_body / qbx_eri_store; getGcore :305-319 ->
+    qbx_fock_build).  ``mode``: "stored" | "direct" | "dense" (default: stored when the packed
+    unique ERIs fit comfortably, else direct).  ``comm``: optional object with
+    ``rank``, ``size`` and ``allreduce(ndarray) -> ndarray`` (multi-GPU: one process per GPU,
+    partial G summed over ranks -- see parallel.py)."""
+    from .integrals import DeviceBasis, DeviceERI, elecKinetics, nucAttractions, overlaps
+
+    if not isinstance(nucInfo, NuclearCluster):
+        nucInfo = NuclearCluster(*nucInfo)
+    config = config or HFconfig()
+    basis = bs if isinstance(bs, DeviceBasis) else DeviceBasis(bs)
+    ne = int(round(nucInfo.charges.sum()))
+    hf = config.HF
+    if hf is None:                                        # HartreeFock.jl:980-983
+        hf = RCHartreeFock() if ne % 2 == 0 else UOHartreeFock()
+    Ns = (ne // 2,) if isinstance(hf, RCHartreeFock) else (ne - ne // 2, ne // 2)
+    if isinstance(hf, RCHartreeFock) and ne % 2:
+        raise ValueError("RCHartreeFock needs an even number of electrons")
+    S = overlaps(basis)
+    Hcore = elecKinetics(basis) + nucAttractions(nucInfo, basis)
+    rank, size = (comm.rank, comm.size) if comm is not None else (0, 1)
+    if mode is None:
+        n = basis.nbf
+        mode = "stored" if (n ** 4 / 8.0) * 8 < 60e9 * size else "direct"
+    eri = DeviceERI(basis, mode=mode, screen_tol=screen_tol, rank=rank, nranks=size)
+
+    def gcore(DJ, DKs):
+        Gs = eri.getGcore(DJ, DKs)
+        if comm is not None and size > 1:
+            Gs = [comm.allreduce(G) for G in Gs]
+        return Gs
+
+    Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCore(S, Hcore, gcore, Ns, config, None, printInfo)
+    return HFfinalInfo((E, nucRepulsion(nucInfo)), Cs, Ds, Fs, tuple(eps), conv, steps, nb,
+                       trace if config.saveTrace else trace[-1:])

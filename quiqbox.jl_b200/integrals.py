@@ -1,0 +1,166 @@
+"""Integral entry points: host-side mirror of src/Integration/Interface.jl on top of the
+C ABI (include/qbx.h).  Same names and argument meaning as the reference:
+
+  elecRepulsion(a, b, c, d)     Interface.jl:331-342   -> qbx_eri_quartets
+  elecRepulsions(bs)            Interface.jl:356-365   -> qbx_eri_tensor
+  overlaps / elecKinetics / nucAttractions / coreHamiltonian   Interface.jl:46-312 -> qbx_one_body
+  DeviceERI                     the `A4 <: AbstractArray{T,4}` handle that replaces the dense
+                                tensor inside ElecHamiltonianConfig (HartreeFock.jl:143-151);
+                                getGcore(HeeI::DeviceERI, DJ, DK) -> qbx_fock_build
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import lib as _l
+from .basis import GTO, MultiOrbitalData, NuclearCluster
+
+
+class DeviceBasis:
+    """Owns a qbx_basis handle (the device copy of a MultiOrbitalData)."""
+
+    def __init__(self, bs):
+        self.data = bs if isinstance(bs, MultiOrbitalData) else MultiOrbitalData.from_orbitals(bs)
+        d = self.data
+        _l.init()
+        h = C.c_void_p()
+        self._arrays = [np.ascontiguousarray(d.cen, dtype=np.float64), np.ascontiguousarray(d.xpn, dtype=np.float64),
+                        np.ascontiguousarray(d.ang, dtype=np.int32), np.ascontiguousarray(d.bf_off, dtype=np.int64),
+                        np.ascontiguousarray(d.bf_prim, dtype=np.int64), np.ascontiguousarray(d.bf_w, dtype=np.float64)]
+        a = self._arrays
+        _l.check(_l.load().qbx_basis_create(d.nprim, _l.ptr(a[0]), _l.ptr(a[1]), _l.ptr(a[2]), d.nbf, _l.ptr(a[3]),
+                                            _l.ptr(a[4]), _l.ptr(a[5]), C.byref(h)))
+        self.handle = h
+        self.nbf = d.nbf
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            _l.load().qbx_basis_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        out = np.zeros(16, dtype=np.int64)
+        _l.check(_l.load().qbx_basis_info(self.handle, _l.ptr(out)))
+        keys = ["nbf", "nshell", "max_l", "class_path", "n_shell_pairs", "n_quartets", "n_values", "stored_bytes",
+                "n_prim_quartets", "model_flops"]
+        return dict(zip(keys, out.tolist()))
+
+    def stats(self, reset=False):
+        out = np.zeros(16)
+        _l.check(_l.load().qbx_stats(self.handle, _l.ptr(out), int(reset)))
+        keys = ["launches", "eri_seconds", "digest_seconds", "prim_quartets", "model_flops", "digest_bytes"]
+        return dict(zip(keys, out.tolist()))
+
+
+def _as_basis(bs) -> DeviceBasis:
+    return bs if isinstance(bs, DeviceBasis) else DeviceBasis(bs)
+
+
+def elecRepulsions(bs) -> np.ndarray:
+    """N^4 tensor, ``T[i,j,k,l] = (ij|kl)`` (chemists' notation), all 8 images filled."""
+    b = _as_basis(bs)
+    n = b.nbf
+    out = np.empty(n ** 4, dtype=np.float64)
+    _l.check(_l.load().qbx_eri_tensor(b.handle, _l.ptr(out), out.nbytes))
+    return out.reshape((n, n, n, n), order="F")
+
+
+def elecRepulsionList(bs, ijkl) -> np.ndarray:
+    b = _as_basis(bs)
+    idx = np.ascontiguousarray(ijkl, dtype=np.int64).reshape(-1, 4)
+    out = np.empty(len(idx), dtype=np.float64)
+    _l.check(_l.load().qbx_eri_quartets(b.handle, len(idx), _l.ptr(idx), _l.ptr(out)))
+    return out
+
+
+def elecRepulsion(a: GTO, b: GTO, c: GTO, d: GTO) -> float:
+    return float(elecRepulsionList([a, b, c, d], [[0, 1, 2, 3]])[0])
+
+
+def _one_body(bs, kind, nuc=None, coords=None):
+    b = _as_basis(bs)
+    n = b.nbf
+    out = np.empty(n * n, dtype=np.float64)
+    if kind == 2:
+        cl = nuc if isinstance(nuc, NuclearCluster) else NuclearCluster(nuc, coords)
+        Z = np.ascontiguousarray(cl.charges)
+        R = np.ascontiguousarray(cl.coordArray)
+        _l.check(_l.load().qbx_one_body(b.handle, 2, len(Z), _l.ptr(Z), _l.ptr(R), _l.ptr(out)))
+    else:
+        _l.check(_l.load().qbx_one_body(b.handle, kind, 0, None, None, _l.ptr(out)))
+    return out.reshape((n, n), order="F")
+
+
+def overlaps(bs):
+    return _one_body(bs, 0)
+
+
+def elecKinetics(bs):
+    return _one_body(bs, 1)
+
+
+def nucAttractions(nuc, coords_or_bs, bs=None):
+    """nucAttractions(nucs, coords, bs) or nucAttractions(NuclearCluster, bs)."""
+    if bs is None:
+        return _one_body(coords_or_bs, 2, nuc)
+    return _one_body(bs, 2, nuc, coords_or_bs)
+
+
+def coreHamiltonian(nuc, coords_or_bs, bs=None):
+    b = _as_basis(bs if bs is not None else coords_or_bs)
+    return elecKinetics(b) + (nucAttractions(nuc, b) if bs is None else nucAttractions(nuc, coords_or_bs, b))
+
+
+class DeviceERI:
+    """Device-resident two-electron integrals of one basis set: the object that stands where
+    the reference keeps ``HeeI::Array{T,4}`` (HartreeFock.jl:189-193).  ``mode``: "stored"
+    (packed unique ERIs in HBM), "direct" (recomputed per Fock build) or "dense" (N^4)."""
+
+    MODES = {"stored": 0, "direct": 1, "dense": 2}
+
+    def __init__(self, bs, mode="stored", screen_tol=1e-12, rank=0, nranks=1):
+        self.basis = _as_basis(bs)
+        self.mode = mode
+        self.rank, self.nranks = rank, nranks
+        _l.check(_l.load().qbx_eri_store(self.basis.handle, float(screen_tol), self.MODES[mode], rank, nranks))
+
+    @property
+    def shape(self):
+        n = self.basis.nbf
+        return (n, n, n, n)
+
+    def recompute(self):
+        _l.check(_l.load().qbx_eri_recompute(self.basis.handle))
+
+    def getGcore(self, DJ: np.ndarray, DKs: Sequence[np.ndarray]):
+        """getGcore(HeeI, DJ, DK) for every DK in ``DKs`` (1 for RHF, 2 for UHF) in one pass
+        (HartreeFock.jl:305-327).  Returns this rank's partial G when nranks > 1."""
+        n = self.basis.nbf
+        nmat = len(DKs)
+        dj = np.asfortranarray(DJ, dtype=np.float64)
+        dk = np.stack([np.asfortranarray(d, dtype=np.float64).ravel(order="F") for d in DKs])
+        G = np.empty((nmat, n * n), dtype=np.float64)
+        _l.check(_l.load().qbx_fock_build(self.basis.handle, nmat, _l.ptr(dj), _l.ptr(dk), _l.ptr(G)))
+        return [G[m].reshape((n, n), order="F") for m in range(nmat)]
+
+
+def getGcore(HeeI: DeviceERI, DJ, DK):
+    """Drop-in for Quiqbox.getGcore (HartreeFock.jl:305-319) on a DeviceERI."""
+    return HeeI.getGcore(DJ, [DK])[0]
+
+
+def boys(T, mmax, table=False) -> np.ndarray:
+    T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+    out = np.empty((len(T), mmax + 1), dtype=np.float64)
+    _l.init()
+    _l.check(_l.load().qbx_boys(len(T), _l.ptr(T), int(mmax), int(bool(table)), _l.ptr(out)))
+    return out
