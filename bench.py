@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on N GPUs of one node.
+
+Workload (BASELINE.json configs[3]): (H2O)_16 / cc-pVDZ RHF, 400 Cartesian basis functions,
+192 shells, 1.72e8 unique shell quartets, 3.2e9 unique contracted ERIs; the shell-quartet
+list is sharded over the ranks (strong scaling: the molecule is fixed).
+
+One *step* = one pass of the hot path over the whole shard:
+    (1) every unique contracted ERI of the shard recomputed by the shell-class kernels into
+        the packed store (qbx_eri_recompute_async), then
+    (2) one RHF Fock build: J/K digestion of the packed store (qbx_fock_build_device) and,
+        for N > 1, the NCCL all-reduce of the partial G matrices.
+`value` = unique contracted ERIs of the whole job / step time (contracted ERIs/s); the Fock
+build alone (stored mode, the per-SCF-iteration cost) is reported as `fock_build_ms`.
+Inputs are resident in HBM; the packed store (25.7 GB at N = 1) is far larger than L2.
+
+`e2e` = the same metric through the C ABI with HOST buffers, every step: qbx_basis_create
+(basis H2D) -> qbx_eri_store (Schwarz bounds, task lists, all ERIs) -> qbx_fock_build
+(densities H2D, G D2H) -> qbx_basis_destroy.
+
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/) on the
+host cores on a bounded sample of the same workload's unique contracted ERIs.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "contracted_eris_per_sec"
+UNIT = "ERIs/s"
+
+
+def workload(name):
+    import quiqbox_b200 as qb
+    from molecules import benzene, h2o, water_cluster
+    if name.startswith("w"):
+        n = int(name[1:])
+        nuc, xyz = water_cluster(n)
+        label = f"(H2O)_{n} cc-pVDZ RHF"
+    elif name == "benzene":
+        nuc, xyz = benzene()
+        label = "benzene cc-pVDZ RHF"
+    else:
+        nuc, xyz = h2o()
+        label = "H2O cc-pVDZ RHF"
+    bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+    return label, nuc, xyz, bs
+
+
+def unique_count(n):
+    m = n * (n + 1) // 2
+    return m * (m + 1) // 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sample(bs, seconds, parallel=True):
+    """Time the CPU oracle on uniformly sampled unique function quartets of the workload."""
+    import oracle
+    import quiqbox_b200 as qb
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs))
+    n = ob.nbf
+    rng = np.random.RandomState(12345)
+    done, t_used, batch = 0, 0.0, 4096
+    ob.eri_list(rng.randint(0, n, size=(256, 4)), parallel)            # warm-up
+    while t_used < seconds:
+        idx = rng.randint(0, n, size=(batch, 4))
+        t0 = time.perf_counter()
+        ob.eri_list(idx, parallel)
+        t_used += time.perf_counter() - t0
+        done += batch
+    return done / t_used, done, t_used
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's algorithm (the reference is pure
+    Julia and cannot be installed here: no julia binary, no network -- see DESIGN.md)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    label, nuc, xyz, bs = workload(args.workload)
+    cores = os.cpu_count()
+    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(bs, per_step)
+    rates, tot_t, tot_n = [], 0.0, 0
+    for _ in range(args.steps):
+        r, n, t = cpu_sample(bs, per_step)
+        rates.append(r); tot_t += t; tot_n += n
+    v = tot_n / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label, "nbf": len(bs), "unique_eris": unique_count(len(bs))},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{tot_n} uniformly sampled contracted ERIs of {label} per run, OpenMP over quartets, "
+                                       "per-primitive-component Obara-Saika as in the reference"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="w16", help="w<N> water cluster | benzene | h2o")
+    ap.add_argument("--screen", type=float, default=1e-12)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import quiqbox_b200 as qb
+    from quiqbox_b200 import lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.init(local)
+    lib = L.load()
+    stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch, NCCL and libqbx
+    torch.cuda.set_stream(stream)
+    L.check(lib.qbx_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    label, nuc, xyz, bs = workload(args.workload)
+    n = len(bs)
+    t0 = time.perf_counter()
+    db = qb.DeviceBasis(bs)
+    eri = qb.DeviceERI(db, mode="stored", screen_tol=args.screen, rank=rank, nranks=world)
+    setup_s = time.perf_counter() - t0
+    info = db.info()
+
+    rng = np.random.RandomState(3)
+    Dh = rng.uniform(-1, 1, (n, n)); Dh = (Dh + Dh.T) / (2 * n)
+    dDJ = torch.from_numpy(2 * Dh).cuda(); dDK = torch.from_numpy(Dh).cuda()
+    dG = torch.zeros(n * n, dtype=torch.float64, device="cuda")
+
+    def step():
+        L.check(lib.qbx_eri_recompute_async(db.handle))
+        L.check(lib.qbx_fock_build_device(db.handle, 1, C.c_void_p(dDJ.data_ptr()), C.c_void_p(dDK.data_ptr()),
+                                          C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_reduce(dG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    st0 = db.stats()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(local) as clk:
+        barrier()
+        ev[0].record(stream)
+        for _ in range(args.steps):
+            step()
+        ev[1].record(stream)
+        barrier()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    st1 = db.stats()
+
+    # Fock build alone (stored-mode digestion + all-reduce): the per-SCF-iteration cost
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    fe[0].record(stream)
+    for _ in range(args.steps):
+        L.check(lib.qbx_fock_build_device(db.handle, 1, C.c_void_p(dDJ.data_ptr()), C.c_void_p(dDK.data_ptr()),
+                                          C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_reduce(dG)
+    fe[1].record(stream)
+    barrier()
+    fock_ms = fe[0].elapsed_time(fe[1]) / args.steps
+
+    # per-class kernel times of one more recompute (CUDA events on the launching stream)
+    L.check(lib.qbx_eri_recompute_async(db.handle))
+    cls = np.zeros((21, 6))
+    L.check(lib.qbx_class_stats(db.handle, L.ptr(cls)))
+    peak = C.c_double()
+    L.check(lib.qbx_fp64_peak(C.byref(peak)))
+
+    # max over ranks / sums over ranks
+    vals = torch.tensor([ms, fock_ms, float(info["n_values"]), float(info["n_quartets"]), float(info["n_prim_quartets"]),
+                         float(info["model_flops"]), float(info["stored_bytes"]), cls[:, 1].sum() * 1e3],
+                        dtype=torch.float64, device="cuda")
+    mx, sm = vals.clone(), vals.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms_max, fock_max, eri_ms_max = mx[0].item(), mx[1].item(), mx[7].item()
+    tot_values, tot_quartets, tot_primq, tot_flops, tot_bytes = (sm[i].item() for i in (2, 3, 4, 5, 6))
+
+    # ---------------- e2e through the C ABI with host buffers (every step: ingest -> ERIs -> Fock -> G on host)
+    e2e = None
+    if not args.no_e2e:
+        L.check(lib.qbx_set_stream(None))
+        eri = None
+        db.close()
+        mod = qb.MultiOrbitalData.from_orbitals(bs)
+        arrs = [np.ascontiguousarray(a) for a in (mod.cen, mod.xpn, mod.ang, mod.bf_off, mod.bf_prim, mod.bf_w)]
+        DJh, DKh, Gh = np.asfortranarray(2 * Dh), np.asfortranarray(Dh), np.zeros((n, n), order="F")
+        h2d = sum(a.nbytes for a in arrs) + DJh.nbytes + DKh.nbytes
+        times = []
+        for it in range(1 + max(1, min(args.steps, 2))):
+            barrier()
+            t0 = time.perf_counter()
+            h = C.c_void_p()
+            L.check(lib.qbx_basis_create(mod.nprim, L.ptr(arrs[0]), L.ptr(arrs[1]), L.ptr(arrs[2]), mod.nbf, L.ptr(arrs[3]),
+                                         L.ptr(arrs[4]), L.ptr(arrs[5]), C.byref(h)))
+            L.check(lib.qbx_eri_store(h, args.screen, 0, rank, world))
+            L.check(lib.qbx_fock_build(h, 1, L.ptr(DJh), L.ptr(DKh), L.ptr(Gh)))
+            if world > 1:
+                g = torch.from_numpy(Gh).cuda(); dist.all_reduce(g); Gh[:] = g.cpu().numpy()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            lib.qbx_basis_destroy(h)
+            if it > 0:
+                times.append(dt)
+        t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": tot_values / t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(Gh.nbytes), "seconds_per_step": t.item(),
+               "path": "qbx_basis_create -> qbx_eri_store(stored) -> qbx_fock_build (host D, host G) -> qbx_basis_destroy"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # dominant kernel = the class kernel with the largest device time
+        k = int(np.argmax(cls[:, 1]))
+        code = int(cls[k, 0])
+        kflops = cls[k, 4] / cls[k, 1] * 1e-12 if cls[k, 1] > 0 else 0.0
+        all_flops = cls[:, 4].sum() / cls[:, 1].sum() * 1e-12
+        digest_gbs = (info["stored_bytes"] / (fock_ms * 1e-3)) * 1e-9
+        per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
+                      "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],
+                      "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0} for r in cls if r[2] > 0]
+        line = {
+            "metric": METRIC, "value": tot_values / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label, "nbf": n, "shells": info["nshell"], "unique_shell_quartets": tot_quartets,
+                       "unique_eris": tot_values, "prim_quartets": tot_primq, "screen_tol": args.screen,
+                       "l2": "inputs larger than L2 (packed store %.1f GB/rank)" % (info["stored_bytes"] * 1e-9),
+                       "parallelism": f"shell-quartet shards x{world}", "setup_seconds": setup_s},
+            "eri_ms": eri_ms_max, "fock_build_ms": fock_max, "fock_build_s_per_iter": fock_max * 1e-3,
+            "gpu_launches": int(round((st1["launches"] - st0["launches"]))),
+            "roofline": {"bound": "fp64", "kernel": f"eri_class_kernel<{code // 1000},{code // 100 % 10},{code // 10 % 10},{code % 10}>",
+                         "achieved": kflops, "peak": peak.value, "unit": "TFLOP/s", "frac": kflops / peak.value if peak.value else None,
+                         "traffic": None, "peak_source": "measured in this run (qbx_fp64_peak, DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
+                         "all_eri_kernels_achieved": all_flops, "all_eri_kernels_frac": all_flops / peak.value if peak.value else None,
+                         "work_model": "SURVEY.md 8(d): flops = prim_quartets*(prim+acc) + quartets*hrr"},
+            "roofline_digest": {"bound": "hbm", "kernel": "digest_kernel<*> (stored-mode Fock build)", "achieved": digest_gbs,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": digest_gbs / hbm_peak, "traffic": None,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "per_class": per_class,
+            "clocks": clk.summary(),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1:
+            t0 = time.perf_counter()
+            v, nd, tu = cpu_sample(bs, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{nd} uniformly sampled contracted ERIs of {label} in {tu:.1f} s, OpenMP over "
+                                              "quartets; per-primitive-component algorithm of the reference"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,24 @@ int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
 int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed,
                    double *secs, double *checksum, int64_t nsample, double *sample_out, double *sample_geom);
 
+/* Asynchronous variant of qbx_eri_recompute: only enqueues the class kernels on the
+ * library's stream (see qbx_set_stream). */
+int qbx_eri_recompute_async(qbx_basis *b);
+
+/* Make every later launch of this process use `stream` (cudaStream_t as void*; NULL restores
+ * the library's own stream).  Lets a host framework (torch.distributed + NCCL) order its
+ * collectives and CUDA events with the library's kernels on one stream. */
+int qbx_set_stream(void *stream);
+
+/* Per-class device times of the most recent qbx_eri_recompute[_async] (synchronises).
+ * out[21][6]: la*1000+lb*100+lc*10+ld, seconds, shell quartets, primitive quartets,
+ * model flops, component values.  Rows follow the canonical class order. */
+int qbx_class_stats(qbx_basis *b, double *out);
+
+/* Measured FP64 FMA peak of the bound device (register-resident DFMA chains, all SMs):
+ * the roofline denominator of the ERI kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int qbx_fp64_peak(double *tflops);
+
 /* counters since the last reset: [0] kernels launched, [1] device seconds in ERI kernels,
  * [2] device seconds in digestion kernels, [3] primitive quartets evaluated,
  * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */

@@ -20,6 +20,7 @@ static int g_device = -1;
 static cudaStream_t g_stream = nullptr;
 static double *g_boys_f = nullptr, *g_boys_e = nullptr;
 
+static cudaStream_t g_own_stream = nullptr;
 cudaStream_t qbx_stream() { return g_stream; }
 BoysTable qbx_boys_table() { return BoysTable{g_boys_f, g_boys_e}; }
 
@@ -64,7 +65,8 @@ extern "C" int qbx_init(int device, int *n_dev_out)
     if (g_device == device) return QBX_OK;
     if (g_device >= 0) { qbx_set_error("qbx_init: this process is already bound to another device"); return QBX_ERR_STATE; }
     QBX_CUDA(cudaSetDevice(device));
-    QBX_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    QBX_CUDA(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
+    g_stream = g_own_stream;
     int rc = build_boys_table();
     if (rc) return rc;
     g_device = device;
@@ -78,8 +80,8 @@ extern "C" int qbx_shutdown(void)
     cudaSetDevice(g_device);
     cudaFree(g_boys_f); cudaFree(g_boys_e);
     g_boys_f = g_boys_e = nullptr;
-    cudaStreamDestroy(g_stream);
-    g_stream = nullptr;
+    cudaStreamDestroy(g_own_stream);
+    g_stream = g_own_stream = nullptr;
     g_device = -1;
     return QBX_OK;
 }
@@ -260,16 +262,81 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
     return QBX_OK;
 }
 
-extern "C" int qbx_eri_recompute(qbx_basis *b)
+extern "C" int qbx_eri_recompute_async(qbx_basis *b)
 {
     if (!b) { qbx_set_error("qbx_eri_recompute: null handle"); return QBX_ERR_ARG; }
     int rc = ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     if (b->mode != 0 || !b->eng) { qbx_set_error("qbx_eri_recompute: call qbx_eri_store(mode = 0) first"); return QBX_ERR_STATE; }
-    rc = b->eng->recompute(g_stream, b->stats);
+    return b->eng->recompute(g_stream, b->stats);
+}
+
+extern "C" int qbx_eri_recompute(qbx_basis *b)
+{
+    int rc = qbx_eri_recompute_async(b);
     if (rc) return rc;
     QBX_CUDA(cudaStreamSynchronize(g_stream));
+    return QBX_OK;
+}
+
+extern "C" int qbx_set_stream(void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    QBX_CUDA(cudaStreamSynchronize(g_stream));
+    g_stream = stream ? (cudaStream_t)stream : g_own_stream;
+    return QBX_OK;
+}
+
+extern "C" int qbx_class_stats(qbx_basis *b, double *out)
+{
+    if (!b || !out) { qbx_set_error("qbx_class_stats: null argument"); return QBX_ERR_ARG; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (!b->eng) { qbx_set_error("qbx_class_stats: basis has no shell-class path"); return QBX_ERR_STATE; }
+    return b->eng->class_stats(out);
+}
+
+// register-resident DFMA chains: 8 independent accumulators per thread
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int qbx_fp64_peak(double *tflops)
+{
+    if (!tflops) { qbx_set_error("qbx_fp64_peak: null argument"); return QBX_ERR_ARG; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    QBX_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double *d = nullptr;
+    QBX_CUDA(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    QBX_CUDA(cudaEventCreate(&e0));
+    QBX_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        QBX_CUDA(cudaEventRecord(e0, g_stream));
+        k_dfma_peak<<<blocks, 256, 0, g_stream>>>(d, iters, 0.999999, 1e-9);
+        QBX_CUDA(cudaEventRecord(e1, g_stream));
+        QBX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        QBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
     return QBX_OK;
 }
 

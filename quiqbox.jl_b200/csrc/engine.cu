@@ -345,6 +345,7 @@ Engine::~Engine()
     for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
+    for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
 }
@@ -524,22 +525,45 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
 int Engine::recompute(cudaStream_t s, double *stats)
 {
     if (mode_ != 0) { qbx_set_error("recompute: stored mode only"); return QBX_ERR_STATE; }
-    QBX_CUDA(cudaEventRecord(ev0_, s));
+    int c = 0;
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
-        for (int kc = 0; kc <= bc; ++kc) {
+        for (int kc = 0; kc <= bc; ++kc, ++c) {
+            if (!cls_ev_[c]) QBX_CUDA(cudaEventCreate(&cls_ev_[c]));
+            QBX_CUDA(cudaEventRecord(cls_ev_[c], s));
             const TaskList &tl = tasks_[bc][kc];
             if (tl.n == 0) continue;
             int rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], s);
             if (rc) return rc;
             stats[0] += 1;
         }
-    QBX_CUDA(cudaEventRecord(ev1_, s));
-    QBX_CUDA(cudaEventSynchronize(ev1_));
-    float ms = 0;
-    QBX_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
-    stats[1] += ms * 1e-3;
+    if (!cls_ev_[QBX_NCLASS]) QBX_CUDA(cudaEventCreate(&cls_ev_[QBX_NCLASS]));
+    QBX_CUDA(cudaEventRecord(cls_ev_[QBX_NCLASS], s));
+    cls_timed_ = true;
     stats[3] += n_primq_;
     stats[4] += model_flops_;
+    return QBX_OK;
+}
+
+int Engine::class_stats(double *out)
+{
+    if (!cls_timed_) { qbx_set_error("qbx_class_stats: no recompute has run"); return QBX_ERR_STATE; }
+    QBX_CUDA(cudaEventSynchronize(cls_ev_[QBX_NCLASS]));
+    int c = 0;
+    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+        for (int kc = 0; kc <= bc; ++kc, ++c) {
+            const ClassOps *ops = qbx_class_ops(bc, kc);
+            const TaskList &tl = tasks_[bc][kc];
+            float ms = 0;
+            QBX_CUDA(cudaEventElapsedTime(&ms, cls_ev_[c], cls_ev_[c + 1]));
+            double *o = out + 6 * c;
+            o[0] = ops->la * 1000 + ops->lb * 100 + ops->lc * 10 + ops->ld;
+            o[1] = ms * 1e-3;
+            o[2] = (double)tl.n;
+            o[3] = tl.nprimq;
+            o[4] = tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
+                   (double)tl.n * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
+            o[5] = (double)tl.n * ops->ncomp;
+        }
     return QBX_OK;
 }
 

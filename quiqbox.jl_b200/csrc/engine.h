@@ -71,7 +71,8 @@ public:
     void info(int64_t *info) const;
     int fill_tensor(double *d_tensor, cudaStream_t s, double *stats);
     int store(double tol, int mode, int rank, int nranks, cudaStream_t s, double *stats);
-    int recompute(cudaStream_t s, double *stats);
+    int recompute(cudaStream_t s, double *stats);          // enqueue only; per-class events recorded
+    int class_stats(double *out);                          // synchronises on the last recompute
     int fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats);
     void release_store();
 
@@ -102,6 +103,8 @@ private:
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t cls_ev_[QBX_NCLASS + 1] = {nullptr};
+    bool cls_timed_ = false;
 };
 
 double qbx_model_flops_prim(int la, int lb, int lc, int ld);   // prim + acc of SURVEY.md 8(d)

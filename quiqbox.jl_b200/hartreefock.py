@@ -16,9 +16,9 @@ Conventions kept from the reference:
   SCF    stages of (:DD | :DIIS | :ADIIS | :EDIIS) with per-stage thresholds; convergence
          |dE| <= thr and RMS(dD) <= ratio*thr, gated by RMS(FDS-SDF) <= ratio*thr (:1171-1174)
 
-The interpolation stages (:ADIIS, :EDIIS) are served by the same commutator-DIIS
-extrapolation as :DIIS: they differ only in the SCF *trajectory*, not in the converged
-energy that parity is defined on (BASELINE.json: 1e-8 Ha).
+LAPACK's eigen and the reference's L-BFGS-B/SPG coefficient solvers are replaced by numpy /
+scipy (SLSQP on the simplex); they shape the SCF *trajectory*, not the converged energy that
+parity is defined on (BASELINE.json: 1e-8 Ha).
 """
 from __future__ import annotations
 
@@ -176,9 +176,56 @@ def _guess(kind, nspin, X, S, Hcore, gcore, Ns, sad):
 
 
 # ---------------------------------------------------------------------------- SCF core
+def _simplex_min(v, B):
+    """argmin_c v.c + c.B.c/2 with c >= 0, sum c = 1 (constraintSolver!, HartreeFock.jl:1416-1485;
+    the reference uses L-BFGS-B / SPG on a reparametrisation, here SLSQP on the simplex)."""
+    from scipy.optimize import minimize
+    m = len(v)
+    Bs = (B + B.T) / 2.0
+    best = None
+    for x0 in (np.full(m, 1.0 / m), np.eye(m)[-1], np.eye(m)[int(np.argmin(v))]):
+        r = minimize(lambda c: v @ c + 0.5 * c @ Bs @ c, x0, jac=lambda c: v + Bs @ c, method="SLSQP",
+                     bounds=[(0.0, 1.0)] * m, constraints=[{"type": "eq", "fun": lambda c: c.sum() - 1.0,
+                                                            "jac": lambda c: np.ones(m)}],
+                     options={"maxiter": 200, "ftol": 1e-14})
+        if best is None or r.fun < best.fun:
+            best = r
+    c = np.clip(best.x, 0.0, None)
+    return c / c.sum()
+
+
+def _xdiis_coeff(method, Ds, Fs, Es, S, X):
+    """DIIScore / EDIIScore / ADIIScore, HartreeFock.jl:1273-1316."""
+    m = len(Ds)
+    if method == "DIIS":
+        errs = [(X.T @ (F @ D @ S - S @ D @ F) @ X).ravel() for F, D in zip(Fs, Ds)]
+        B = -np.ones((m + 1, m + 1)); B[m, m] = 0.0
+        for a in range(m):
+            for b in range(m):
+                B[a, b] = errs[a] @ errs[b]
+        rhs = np.zeros(m + 1); rhs[m] = -1.0
+        try:
+            return np.linalg.solve(B, rhs)[:m]
+        except np.linalg.LinAlgError:
+            c = np.zeros(m); c[-1] = 1.0
+            return c
+    if method == "EDIIS":
+        v = np.array(Es)
+        B = np.array([[-np.vdot(Ds[i] - Ds[j], Fs[i] - Fs[j]) for j in range(m)] for i in range(m)])
+    else:                                                    # ADIIS
+        v = np.array([np.vdot(Ds[i] - Ds[-1], Fs[-1]) for i in range(m)])
+        B = np.array([[np.vdot(Ds[i] - Ds[-1], Fs[j] - Fs[-1]) for j in range(m)] for i in range(m)])
+    return _simplex_min(v, B)
+
+
 def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFconfig,
                        sad: Optional[Callable] = None, printInfo=False):
-    """HartreeFock.jl:1049-1228 on top of an abstract ``gcore`` (the hot-path call)."""
+    """HartreeFock.jl:1049-1228 on top of an abstract ``gcore`` (the hot-path call).
+
+    Stages follow SCFconfig: :DD is damped direct diagonalisation (:1245-1270); :DIIS, :EDIIS
+    and :ADIIS extrapolate F = sum c_i F_i from a per-spin history of (D, F, E) of size 10
+    (xDIIScore! :1318-1394, incl. its reset-on-energy-rise and drop-highest-energy rules) and
+    then run getCDFE (:392-403)."""
     nspin = len(Ns)
     X = getOrthonormalization(S)
     nbuild = [0]
@@ -187,60 +234,60 @@ def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFc
         nbuild[0] += 1
         return gcore(DJ, DKs)
 
+    def cdfe(Fin):
+        sol = [getC(X, F) for F in Fin]
+        Cn = tuple(s[0] for s in sol)
+        Dn = tuple(getD(C, n) for C, n in zip(Cn, Ns))
+        Fn = tuple(Hcore + G for G in getG(gc, Dn))
+        En = tuple(getE(Hcore, F, D) for F, D in zip(Fn, Dn))
+        return Cn, Dn, Fn, En, [s[1] for s in sol]
+
     Cs = _guess(config.initial, nspin, X, S, Hcore, gc, Ns, sad)
     Ds = tuple(getD(C, n) for C, n in zip(Cs, Ns))
     Fs = tuple(Hcore + G for G in getG(gc, Ds))
-    Etot = get2SpinQuantity([getE(Hcore, F, D) for F, D in zip(Fs, Ds)])
+    Es = tuple(getE(Hcore, F, D) for F, D in zip(Fs, Ds))
+    Etot = get2SpinQuantity(Es)
     trace = [Etot]
+    # shared (D, F, E) history per spin sector, as HFtempInfo keeps it (:419-436)
+    hist = [dict(D=[Ds[s]], F=[Fs[s]], E=[Es[s]]) for s in range(nspin)]
     ratioD, ratioF = config.strategy.secondaryConvRatio
     step, converged = 0, False
     eps = [None] * nspin
+    stages = config.strategy.stages()
+    resetThreshold = 1000 * 4e-16
 
-    def err_vec(Fs_, Ds_):
-        return [X.T @ (F @ D @ S - S @ D @ F) @ X for F, D in zip(Fs_, Ds_)]
-
-    for method, thr in config.strategy.stages():
-        histF: List[Tuple[np.ndarray, ...]] = []
-        histE: List[np.ndarray] = []
+    for si, (method, thr) in enumerate(stages):
         stage_done = False
+        for h in hist:                                        # a new stage starts from the recent history
+            for k in ("D", "F", "E"):
+                h[k] = h[k][-defaultDIISsize:]
         while step < config.maxStep:
             step += 1
             if method == "DD":
-                # directDiag, HartreeFock.jl:1245-1251 then getCDFE on F[D_damped] (:1265)
-                Dn = tuple((1 - defaultDS) * getD(getC(X, F)[0], n) + defaultDS * D
-                           for F, D, n in zip(Fs, Ds, Ns))
+                Dn = tuple((1 - defaultDS) * getD(getC(X, F)[0], n) + defaultDS * D for F, D, n in zip(Fs, Ds, Ns))
                 Fin = tuple(Hcore + G for G in getG(gc, Dn))
             else:
-                histF.append(Fs)
-                histE.append(np.concatenate([e.ravel() for e in err_vec(Fs, Ds)]))
-                histF, histE = histF[-defaultDIISsize:], histE[-defaultDIISsize:]
-                m = len(histF)
-                if m > 1:
-                    B = -np.ones((m + 1, m + 1)); B[m, m] = 0.0
-                    for a in range(m):
-                        for b in range(m):
-                            B[a, b] = histE[a] @ histE[b]
-                    rhs = np.zeros(m + 1); rhs[m] = -1.0
-                    try:
-                        c = np.linalg.solve(B, rhs)[:m]
-                    except np.linalg.LinAlgError:
-                        c = np.zeros(m); c[-1] = 1.0
-                    Fin = tuple(sum(c[a] * histF[a][s] for a in range(m)) for s in range(nspin))
-                else:
-                    Fin = Fs
-            # getCDFE, HartreeFock.jl:392-403
-            sol = [getC(X, F) for F in Fin]
-            Cn = tuple(s[0] for s in sol)
-            eps = [s[1] for s in sol]
-            Dn2 = tuple(getD(C, n) for C, n in zip(Cn, Ns))
-            Fn = tuple(Hcore + G for G in getG(gc, Dn2))
-            En = get2SpinQuantity([getE(Hcore, F, D) for F, D in zip(Fn, Dn2)])
-            dE = En - Etot
-            Dt_old = sum(Ds) * (2.0 if nspin == 1 else 1.0)
-            Dt_new = sum(Dn2) * (2.0 if nspin == 1 else 1.0)
-            dD = float(np.sqrt(np.mean((Dt_new - Dt_old) ** 2)))
-            Cs, Ds, Fs, Etot = Cn, Dn2, Fn, En
-            dF = float(np.sqrt(np.mean(np.concatenate([e.ravel() for e in err_vec(Fs, Ds)]) ** 2)))
+                Fin = []
+                for h in hist:
+                    c = _xdiis_coeff(method, h["D"], h["F"], h["E"], S, X) if len(h["D"]) > 1 else np.ones(1)
+                    Fin.append(sum(ci * Fi for ci, Fi in zip(c, h["F"])))
+            Cn, Dn2, Fn, En, eps = cdfe(Fin)
+            for s, h in enumerate(hist):
+                h["D"].append(Dn2[s]); h["F"].append(Fn[s]); h["E"].append(En[s])
+                if method != "DD" and len(h["E"]) > 2 and h["E"][-1] - h["E"][-2] > resetThreshold:
+                    for k in ("D", "F", "E"):
+                        h[k] = h[k][-2:-1]
+                elif len(h["E"]) > defaultDIISsize:
+                    drop = int(np.argmax(h["E"]))
+                    for k in ("D", "F", "E"):
+                        h[k].pop(drop)
+            Enew = get2SpinQuantity(En)
+            dE = Enew - Etot
+            w = 2.0 if nspin == 1 else 1.0
+            dD = float(np.sqrt(np.mean((w * sum(Dn2) - w * sum(Ds)) ** 2)))
+            Cs, Ds, Fs, Etot = Cn, Dn2, Fn, Enew
+            dF = float(np.sqrt(np.mean(np.concatenate(
+                [(X.T @ (F @ D @ S - S @ D @ F) @ X).ravel() for F, D in zip(Fs, Ds)]) ** 2)))
             trace.append(Etot)
             if printInfo:
                 print(f"| {step:4d} | {method:5s} | {Etot: .12f} | {dE: .3e} | {dF:.3e} | {dD:.3e}")
@@ -249,7 +296,7 @@ def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFc
                 break
         if not stage_done:
             break
-        converged = True if (method, thr) == config.strategy.stages()[-1] else converged
+        converged = (si == len(stages) - 1)
     return Cs, Ds, Fs, eps, Etot, converged, step, nbuild[0], trace
 
 

@@ -24,6 +24,10 @@ SIGNATURES = {
     "qbx_eri_quartets": [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     "qbx_eri_store": [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int],
     "qbx_eri_recompute": [C.c_void_p],
+    "qbx_eri_recompute_async": [C.c_void_p],
+    "qbx_set_stream": [C.c_void_p],
+    "qbx_class_stats": [C.c_void_p, C.c_void_p],
+    "qbx_fp64_peak": [C.c_void_p],
     "qbx_fock_build": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_fock_build_device": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_one_body": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
