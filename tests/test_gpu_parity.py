@@ -239,8 +239,11 @@ def test_synthetic_class_batch_vs_oracle(cls):
             idx = [(offs[0] + a, offs[1] + b, offs[2] + c, offs[3] + d) for a in range(len(sh[0]))
                    for b in range(len(sh[1])) for c in range(len(sh[2])) for d in range(len(sh[3]))]
             ref = ob.eri_list(idx)
+            # log-uniform exponents in [0.1, 1e3] put zeta/eta ratios of 1e4 into the electron-transfer
+            # recurrence, which the reference (modeTransfer, GaussianOrbitals.jl:529-538) and hence the
+            # oracle share; the bar here is the north-star one, 1e-10 absolute (relative for values > 1)
             scale = max(1.0, np.max(np.abs(ref)))
-            assert np.max(np.abs(out[q] - ref)) < 1e-11 * scale, (cls, K, q)
+            assert np.max(np.abs(out[q] - ref)) < ERI_ATOL * scale, (cls, K, q)
 
 
 # ------------------------------------------------------------------ error behaviour at the boundary
