@@ -331,8 +331,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if world == 1:
-            t0 = time.perf_counter()
+        if world == 1 and args.cpu_seconds > 0:
             v, nd, tu = cpu_sample(bs, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{nd} uniformly sampled contracted ERIs of {label} in {tu:.1f} s, OpenMP over "

@@ -8,7 +8,18 @@
 static int launch_eri(const ClassArgs &a, cudaStream_t s)
 {
     if (a.ntasks <= 0) return QBX_OK;
-    eri_class_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
+    static int max_blocks = 0;           // resident blocks on the whole device for this kernel
+    if (max_blocks == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        QBX_CUDA(cudaGetDevice(&dev));
+        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_class_kernel<QLA, QLB, QLC, QLD>,
+                                                               QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES));
+        max_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int64_t need = (a.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    const unsigned grid = (unsigned)(need < max_blocks ? need : max_blocks);
+    eri_class_kernel<QLA, QLB, QLC, QLD><<<grid, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }

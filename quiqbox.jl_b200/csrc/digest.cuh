@@ -16,18 +16,30 @@
 #pragma once
 #include "engine.h"
 
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 template <int LA, int LB, int LC, int LD>
 __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
 {
     constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD);
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= p.ntasks) return;
+    const int64_t q0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q0 - (threadIdx.x & 31) >= p.ntasks) return;          // whole warp past the end
+    const bool valid = q0 < p.ntasks;
+    const int64_t q = valid ? q0 : p.ntasks - 1;
     const int2 t = p.tasks[q];
     const int2 sb = p.bra_shells[t.x], sk = p.ket_shells[t.y];
-    double f = 1.0;
+    double f = valid ? 1.0 : 0.0;
     if (sb.x == sb.y) f *= 0.5;
     if (sk.x == sk.y) f *= 0.5;
     if (p.same_class && t.x == t.y) f *= 0.5;
+    // tasks are bra-major, so a warp nearly always shares its bra pair: J_AB is then reduced
+    // over the warp and added once (the same-address atomics were the bottleneck otherwise)
+    const bool uni = __all_sync(0xffffffffu, t.x == __shfl_sync(0xffffffffu, t.x, 0));
     int fa[NA], fb[NB], fc[NCc], fd[ND];
 #pragma unroll
     for (int i = 0; i < NA; ++i) fa[i] = p.shell_bf[6 * sb.x + i];
@@ -48,20 +60,27 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
     for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            if (fa[a] < 0 || fb[b] < 0) continue;
-            const double dab = p.DJ[fa[a] + N * fb[b]];
+            const bool okab = fa[a] >= 0 && fb[b] >= 0;
+            const double dab = okab ? p.DJ[fa[a] + N * fb[b]] : 0.0;
             double jab = 0.0;
 #pragma unroll
             for (int c = 0; c < NCc; ++c)
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    if (fc[c] < 0 || fd[d] < 0) continue;
+                    if (!okab || fc[c] < 0 || fd[d] < 0) continue;
                     const double v = vq[(int64_t)(((a * NB + b) * NCc + c) * ND + d) * p.ntasks];
                     jab = fma(p.DJ[fc[c] + N * fd[d]], v, jab);
                     jcd[c * ND + d] = fma(dab, v, jcd[c * ND + d]);
                 }
-            atomicAdd(p.Jt + fa[a] + N * fb[b], 2.0 * f * jab);
+            jab *= 2.0 * f;
+            if (uni) {
+                jab = warp_sum(jab);
+                if ((threadIdx.x & 31) == 0 && okab) atomicAdd(p.Jt + fa[a] + N * fb[b], jab);
+            } else if (okab && valid) {
+                atomicAdd(p.Jt + fa[a] + N * fb[b], jab);
+            }
         }
+    if (!valid) return;
 #pragma unroll
     for (int c = 0; c < NCc; ++c)
 #pragma unroll

@@ -293,7 +293,32 @@ static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::
         poff[n + 1] = poff[n] + (int)prims[i].size();
         out.h_nprim[n] = (int)prims[i].size();
     }
+    // transposed copy for coalesced ket-side loads (see PairSet in eri_class.cuh)
+    std::vector<double> soa((size_t)QBX_SOA_NF * poff.back(), 0.0);
+    std::vector<int2> soa_idx(sp.size());
+    {
+        size_t base = 0, g0 = 0;
+        while (g0 < sp.size()) {
+            size_t g1 = g0;
+            while (g1 < sp.size() && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
+            const size_t g = g1 - g0, np = (size_t)out.h_nprim[g0];
+            for (size_t j = g0; j < g1; ++j) {
+                soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
+                for (size_t pp = 0; pp < np; ++pp) {
+                    const double *r = prim.data() + 8 * ((size_t)poff[j] + pp);
+                    const double f[QBX_SOA_NF] = {r[0], r[1], r[2], r[3], r[4], r[5], r[6]};
+                    for (int k = 0; k < QBX_SOA_NF; ++k) soa[base + (pp * QBX_SOA_NF + k) * g + (j - g0)] = f[k];
+                }
+            }
+            base += g * np * QBX_SOA_NF;
+            g0 = g1;
+        }
+    }
     out.la = la; out.lb = lb; out.npair = (int)sp.size(); out.nprim = poff.back();
+    QBX_CUDA(cudaMalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
+    QBX_CUDA(cudaMalloc(&out.soa_idx, std::max<size_t>(1, soa_idx.size()) * sizeof(int2)));
+    if (!soa.empty()) QBX_CUDA(cudaMemcpy(out.soa, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (!soa_idx.empty()) QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), soa_idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
     QBX_CUDA(cudaMalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
     QBX_CUDA(cudaMalloc(&out.prim_off, poff.size() * sizeof(int)));
     QBX_CUDA(cudaMalloc(&out.geom, std::max<size_t>(1, geom.size()) * sizeof(double)));
@@ -342,7 +367,7 @@ int Engine::upload(bool pair_adjacent)
 Engine::~Engine()
 {
     release_store();
-    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); }
+    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);

@@ -50,9 +50,10 @@ struct DevPairSet {
     int la = 0, lb = 0, npair = 0, nprim = 0;
     int2 *shells = nullptr;
     int *prim_off = nullptr;
-    double *geom = nullptr, *prim = nullptr, *schwarz = nullptr;
+    double *geom = nullptr, *prim = nullptr, *schwarz = nullptr, *soa = nullptr;
+    int2 *soa_idx = nullptr;
     std::vector<int> h_nprim;            // primitive pairs per pair (host copy, for cost models)
-    PairSet view() const { return PairSet{shells, prim_off, geom, prim, npair}; }
+    PairSet view() const { return PairSet{shells, prim_off, geom, prim, soa, soa_idx, npair}; }
 };
 
 struct TaskList {

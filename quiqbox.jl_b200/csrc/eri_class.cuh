@@ -56,11 +56,19 @@ template <int LA, int E, int LC, int F> struct ALay {
 //   K  = sqrt(2) pi^(5/4) c_a c_b exp(-a b |AB|^2 / zeta) / zeta      (GaussianOrbitals.jl:627-629)
 //   xr = exponent of the right-hand primitive (b or d), needed by the electron transfer
 // pair geometry record (8 doubles): A(3), A-B(3), pad(2)
+// The same primitive data also exists transposed ("SoA") for the ket side: pairs are sorted
+// by their number of primitive pairs, and inside a run of g pairs with equal count the
+// field f of primitive p of the j-th pair of the run sits at soa[base + (p*7 + f)*g + j], so
+// that the lanes of a warp (consecutive kets) read consecutive addresses.
+// Fields: eta, Qx, Qy, Qz, K, d, 1/(2 eta).
+#define QBX_SOA_NF 7
 struct PairSet {
     const int2 *shells;        // (A, B) shell ids per pair
     const int *prim_off;       // [npair + 1]
     const double *geom;        // [npair][8]
-    const double *prim;        // [nprimpair][8]
+    const double *prim;        // [nprimpair][8]   AoS (bra side: warp-uniform loads)
+    const double *soa;         // transposed copy  (ket side: coalesced loads)
+    const int2 *soa_idx;       // [npair] (base + j, g)
     int npair;
 };
 
@@ -85,10 +93,14 @@ template <int LX, int LY, class In, class Out>
 __device__ __forceinline__ void hrr_apply(const In &in, const double (&AB)[3], const Out &out)
 {
     double t0[LY + 1][NC(LX + LY)];
+    // (loop bounds are kept independent of outer loop variables and guarded instead: a bound
+    //  like NC(e) is quadratic in the outer index, which stops nvcc from fully unrolling the
+    //  inner loop and would push every array touched here into local memory)
 #pragma unroll
     for (int d = 0; d <= LY; ++d)
 #pragma unroll
-        for (int c = 0; c < NC(LX + d); ++c) t0[d][c] = in(LX + d, c);
+        for (int c = 0; c < NC(LX + LY); ++c)
+            if (c < NC(LX + d)) t0[d][c] = in(LX + d, c);
     if constexpr (LY == 0) {
 #pragma unroll
         for (int c = 0; c < NC(LX); ++c) out(c, 0, t0[0][c]);
@@ -140,7 +152,7 @@ struct EriClass {
     static constexpr int NKET = NCSUM(LC, F);       // stacked ket components after contraction
 
     // one primitive shell quartet: acc += [e0|f0]
-    static __device__ __forceinline__ void primitive(double (&acc)[AL::total], const BoysTable &tb, double zeta,
+    static __device__ __forceinline__ void primitive(double (&acc)[AL::total], const double *tb, double zeta,
                                                      const double (&P)[3], double Kab, const double (&PA)[3],
                                                      double i2z, const double (&bAB)[3], double eta,
                                                      const double (&Q)[3], double Kcd, double i2e,
@@ -188,7 +200,8 @@ struct EriClass {
 #pragma unroll
                 for (int e = LA; e <= E; ++e)
 #pragma unroll
-                    for (int c = 0; c < NC(e); ++c) acc[AL::off(0, e) + c] += V[VL::off(e) + c];
+                    for (int c = 0; c < NC(E); ++c)
+                        if (c < NC(e)) acc[AL::off(0, e) + c] += V[VL::off(e) + c];
             } else {
                 // electron transfer to centre C at m = 0
                 double W[WL::total];
@@ -241,9 +254,9 @@ struct EriClass {
 #pragma unroll
                     for (int e = LA; e <= E; ++e)
 #pragma unroll
-                        for (int c = 0; c < NC(f) * NC(e); ++c) {
+                        for (int c = 0; c < NC(F) * NC(E); ++c) {
                             if (f == 0) { if (c < NC(e)) acc[AL::off(0, e) + c] += V[VL::off(e) + c]; }
-                            else acc[AL::off(f, e) + c] += W[WL::off(f, e) + c];
+                            else if (c < NC(f) * NC(e)) acc[AL::off(f, e) + c] += W[WL::off(f, e) + c];
                         }
             }
         }
@@ -259,7 +272,8 @@ struct EriClass {
 #pragma unroll
         for (int f = LC; f <= F; ++f)
 #pragma unroll
-            for (int cf = 0; cf < NC(f); ++cf) {
+            for (int cf = 0; cf < NC(F); ++cf) {
+                if (cf >= NC(f)) continue;
                 const int kk = NCSUM(LC, f - 1) + cf;
                 hrr_apply<LA, LB>([&](int e, int c) { return acc[AL::off(f, e) + cf * NC(e) + c]; }, AB,
                                   [&](int a, int b, double v) { X[kk][a * NB + b] = v; });
@@ -275,36 +289,46 @@ struct EriClass {
     }
 };
 
+#define QBX_ERI_THREADS 256
+
+// Persistent blocks: the Boys columns of this class are staged in shared memory once, then
+// the block walks the task list with a grid stride (tasks are sorted by cost, so the stride
+// interleaves heavy and light chunks over the SMs).
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(128) eri_class_kernel(ClassArgs p)
+__global__ void __launch_bounds__(QBX_ERI_THREADS) eri_class_kernel(ClassArgs p)
 {
     using EC = EriClass<LA, LB, LC, LD>;
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= p.ntasks) return;
-    const int2 t = p.tasks[q];
-    const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
-    const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
-    const double CD[3] = {gk[3], gk[4], gk[5]};
-    const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
-    const int pk0 = p.ket.prim_off[t.y], pk1 = p.ket.prim_off[t.y + 1];
-    double acc[EC::AL::total];
+    extern __shared__ double boys_smem[];
+    boys_stage_smem<EC::L>(p.boys, boys_smem);
+    __syncthreads();
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < p.ntasks; q += (int64_t)gridDim.x * blockDim.x) {
+        const int2 t = p.tasks[q];
+        const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
+        const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
+        const double CD[3] = {gk[3], gk[4], gk[5]};
+        const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
+        const int nk = p.ket.prim_off[t.y + 1] - p.ket.prim_off[t.y];
+        const int2 si = p.ket.soa_idx[t.y];
+        double acc[EC::AL::total];
 #pragma unroll
-    for (int i = 0; i < EC::AL::total; ++i) acc[i] = 0.0;
-    for (int pb = pb0; pb < pb1; ++pb) {
-        const double4 b0 = ldg4(p.bra.prim + 8 * (int64_t)pb);
-        const double4 b1 = ldg4(p.bra.prim + 8 * (int64_t)pb + 4);
-        const double zeta = b0.x, P[3] = {b0.y, b0.z, b0.w}, Kab = b1.x, i2z = b1.z;
-        const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
-        const double bAB[3] = {b1.y * AB[0], b1.y * AB[1], b1.y * AB[2]};
-        for (int pk = pk0; pk < pk1; ++pk) {
-            const double4 k0 = ldg4(p.ket.prim + 8 * (int64_t)pk);
-            const double4 k1 = ldg4(p.ket.prim + 8 * (int64_t)pk + 4);
-            const double Q[3] = {k0.y, k0.z, k0.w};
-            const double dCD[3] = {k1.y * CD[0], k1.y * CD[1], k1.y * CD[2]};
-            EC::primitive(acc, p.boys, zeta, P, Kab, PA, i2z, bAB, k0.x, Q, k1.x, k1.z, dCD);
+        for (int i = 0; i < EC::AL::total; ++i) acc[i] = 0.0;
+        for (int pb = pb0; pb < pb1; ++pb) {
+            const double4 b0 = ldg4(p.bra.prim + 8 * (int64_t)pb);
+            const double4 b1 = ldg4(p.bra.prim + 8 * (int64_t)pb + 4);
+            const double zeta = b0.x, P[3] = {b0.y, b0.z, b0.w}, Kab = b1.x, i2z = b1.z;
+            const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+            const double bAB[3] = {b1.y * AB[0], b1.y * AB[1], b1.y * AB[2]};
+            const double *kp = p.ket.soa + si.x;
+            for (int pk = 0; pk < nk; ++pk, kp += QBX_SOA_NF * si.y) {
+                const double eta = __ldg(kp);
+                const double Q[3] = {__ldg(kp + si.y), __ldg(kp + 2 * si.y), __ldg(kp + 3 * si.y)};
+                const double Kcd = __ldg(kp + 4 * si.y), dx = __ldg(kp + 5 * si.y), i2e = __ldg(kp + 6 * si.y);
+                const double dCD[3] = {dx * CD[0], dx * CD[1], dx * CD[2]};
+                EC::primitive(acc, boys_smem, zeta, P, Kab, PA, i2z, bAB, eta, Q, Kcd, i2e, dCD);
+            }
         }
+        const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
+        EC::finish(acc, AB, CD, p.shell_scale + 6 * sb.x, p.shell_scale + 6 * sb.y, p.shell_scale + 6 * sk.x,
+                   p.shell_scale + 6 * sk.y, p.out + q, p.ntasks);
     }
-    const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
-    EC::finish(acc, AB, CD, p.shell_scale + 6 * sb.x, p.shell_scale + 6 * sb.y, p.shell_scale + 6 * sk.x,
-               p.shell_scale + 6 * sk.y, p.out + q, p.ntasks);
 }

@@ -319,7 +319,7 @@ __global__ void k_boys(int64_t n, const double *T, int mmax, int table, BoysTabl
     if (t >= n) return;
     if (table) {
         double F[9];
-        boys_table<8>(tb, T[t], 1.0, F);
+        boys_table_global<8>(tb, T[t], 1.0, F);
         for (int m = 0; m <= mmax; ++m) out[(int64_t)(mmax + 1) * t + m] = F[m];
     } else {
         double F[129];
