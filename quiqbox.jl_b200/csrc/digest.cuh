@@ -23,6 +23,36 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Lanes of a warp that update the same G block (same ket shell C or D) are summed first:
+// 32 same-address atomics in one instruction serialise in L2, one atomic per group does not.
+struct KeyGroup {
+    unsigned peers;
+    int rank, steps;
+    int src[5];
+};
+__device__ __forceinline__ KeyGroup make_group(int key)
+{
+    const int lane = threadIdx.x & 31;
+    KeyGroup g;
+    g.peers = __match_any_sync(0xffffffffu, key);
+    g.rank = __popc(g.peers & ((1u << lane) - 1u));
+    int size = __popc(g.peers);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) size = max(size, __shfl_xor_sync(0xffffffffu, size, o));
+    g.steps = size > 1 ? 32 - __clz(size - 1) : 0;             // warp-uniform tree depth
+#pragma unroll
+    for (int k = 0; k < 5; ++k) g.src[k] = (int)__fns(g.peers, lane, (1 << k) + 1);   // (1<<k)-th peer above me or -1
+    return g;
+}
+__device__ __forceinline__ double group_sum(double v, const KeyGroup &g)
+{
+    for (int k = 0; k < g.steps; ++k) {
+        const double up = __shfl_sync(0xffffffffu, v, g.src[k] & 31);
+        if (g.src[k] >= 0 && (g.rank & ((2 << k) - 1)) == 0) v += up;
+    }
+    return v;                                                   // total lives in the rank-0 lane
+}
+
 template <int LA, int LB, int LC, int LD>
 __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
 {
@@ -80,12 +110,18 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
                 atomicAdd(p.Jt + fa[a] + N * fb[b], jab);
             }
         }
-    if (!valid) return;
+    if (valid) {
 #pragma unroll
-    for (int c = 0; c < NCc; ++c)
+        for (int c = 0; c < NCc; ++c)
 #pragma unroll
-        for (int d = 0; d < ND; ++d)
-            if (fc[c] >= 0 && fd[d] >= 0) atomicAdd(p.Jt + fc[c] + N * fd[d], 2.0 * f * jcd[c * ND + d]);
+            for (int d = 0; d < ND; ++d)
+                if (fc[c] >= 0 && fd[d] >= 0) atomicAdd(p.Jt + fc[c] + N * fd[d], 2.0 * f * jcd[c * ND + d]);
+    }
+    // exchange blocks K[A,C], K[B,C] are shared by the lanes with the same C (given the common
+    // bra), K[A,D], K[B,D] by those with the same D; without a common bra nothing is merged
+    const int lane = threadIdx.x & 31;
+    const KeyGroup gC = make_group(uni && valid ? sk.x : -1 - lane);
+    const KeyGroup gD = make_group(uni && valid ? sk.y : -1 - lane);
 
     // exchange part, one density at a time
     for (int m = 0; m < p.nmat; ++m) {
@@ -120,23 +156,31 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int c = 0; c < NCc; ++c)
-                if (fa[a] >= 0 && fc[c] >= 0) atomicAdd(Kt + fa[a] + N * fc[c], f * kac[a * NCc + c]);
+            for (int c = 0; c < NCc; ++c) {
+                const double v = group_sum(f * kac[a * NCc + c], gC);
+                if (valid && gC.rank == 0 && fa[a] >= 0 && fc[c] >= 0) atomicAdd(Kt + fa[a] + N * fc[c], v);
+            }
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int c = 0; c < NCc; ++c) {
+                const double v = group_sum(f * kbc[b * NCc + c], gC);
+                if (valid && gC.rank == 0 && fb[b] >= 0 && fc[c] >= 0) atomicAdd(Kt + fb[b] + N * fc[c], v);
+            }
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int d = 0; d < ND; ++d)
-                if (fa[a] >= 0 && fd[d] >= 0) atomicAdd(Kt + fa[a] + N * fd[d], f * kad[a * ND + d]);
+            for (int d = 0; d < ND; ++d) {
+                const double v = group_sum(f * kad[a * ND + d], gD);
+                if (valid && gD.rank == 0 && fa[a] >= 0 && fd[d] >= 0) atomicAdd(Kt + fa[a] + N * fd[d], v);
+            }
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int c = 0; c < NCc; ++c)
-                if (fb[b] >= 0 && fc[c] >= 0) atomicAdd(Kt + fb[b] + N * fc[c], f * kbc[b * NCc + c]);
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int d = 0; d < ND; ++d)
-                if (fb[b] >= 0 && fd[d] >= 0) atomicAdd(Kt + fb[b] + N * fd[d], f * kbd[b * ND + d]);
+            for (int d = 0; d < ND; ++d) {
+                const double v = group_sum(f * kbd[b * ND + d], gD);
+                if (valid && gD.rank == 0 && fb[b] >= 0 && fd[d] >= 0) atomicAdd(Kt + fb[b] + N * fd[d], v);
+            }
     }
 }
 

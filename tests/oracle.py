@@ -129,3 +129,9 @@ def getGcore(H, DJ, DK):
 def gcore_from_tensor(H):
     """Adapter with the signature hartreefock.runHartreeFockCore expects."""
     return lambda DJ, DKs: [getGcore(H, DJ, DK) for DK in DKs]
+
+
+def getGcore_general(H, DJ, DK):
+    """Same contraction as getGcore for a tensor WITHOUT permutational symmetry (used by the
+    multi-rank CPU test, where each rank holds a slice): every (mu, nu) computed, no mirroring."""
+    return np.einsum("sl,mnls->mn", DJ, H) - np.einsum("ls,mlsn->mn", DK, H)
