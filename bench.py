@@ -267,7 +267,7 @@ def main():
         db.close()
         mod = qb.MultiOrbitalData.from_orbitals(bs)
         arrs = [np.ascontiguousarray(a) for a in (mod.cen, mod.xpn, mod.ang, mod.bf_off, mod.bf_prim, mod.bf_w)]
-        DJh, DKh, Gh = np.asfortranarray(2 * Dh), np.asfortranarray(Dh), np.zeros((n, n), order="F")
+        DJh, DKh, Gh = np.asfortranarray(2 * Dh), np.asfortranarray(Dh), np.zeros(n * n)
         h2d = sum(a.nbytes for a in arrs) + DJh.nbytes + DKh.nbytes
         times = []
         for it in range(1 + max(1, min(args.steps, 2))):
