@@ -1,6 +1,6 @@
 """Builds quiqbox.jl_b200/libqbx.so (sm_100a only) from csrc/ with nvcc, in-tree.
 
-21 per-class translation units (class_inst.cu compiled with -DQLA.. macros) + 3 host/generic
+21 per-class translation units (class_inst.cu compiled with -DQLA.. macros) + 4 host/generic
 units, compiled in parallel, then linked into one shared library whose exported symbols are
 exactly include/qbx.h.  Incremental: a unit is rebuilt when its sources are newer than its
 object.  `python quiqbox.jl_b200/build.py [-j N] [--force]`.
@@ -44,7 +44,7 @@ def build(jobs=None, force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     work, objs = [], []
-    for name in ("api", "generic", "engine"):
+    for name in ("api", "generic", "engine", "eri_coop"):
         src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):

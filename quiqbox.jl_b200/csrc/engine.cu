@@ -8,6 +8,7 @@
 #include <map>
 #include <numeric>
 #include <random>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------ class registry
 #define QBX_DECL(a, b, c, d) extern const ClassOps qbx_ops_##a##b##c##d;
@@ -412,6 +413,14 @@ int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, c
     a.tasks = tasks; a.ntasks = n; a.out = out;
     a.shell_scale = d_shell_scale_;
     a.boys = qbx_boys_table();
+    // Large classes (>= coop_min contracted accumulators per quartet) go to the warp-cooperative
+    // kernel; QBX_COOP_MIN_ACC overrides the threshold (0 = every class, for tests).
+    static const int coop_min = getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : 180;
+    const int nacc = NCSUM(ops->la, ops->la + ops->lb) * NCSUM(ops->lc, ops->lc + ops->ld);
+    if (nacc >= coop_min) {
+        const int rc = qbx_launch_eri_coop(ops->la, ops->lb, ops->lc, ops->ld, a, s);
+        if (rc >= 0) return rc;
+    }
     return ops->eri(a, s);
 }
 

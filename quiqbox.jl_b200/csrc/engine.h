@@ -108,5 +108,6 @@ private:
     bool cls_timed_ = false;
 };
 
+int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cudaStream_t s);   // eri_coop.cu
 double qbx_model_flops_prim(int la, int lb, int lc, int ld);   // prim + acc of SURVEY.md 8(d)
 double qbx_model_flops_hrr(int la, int lb, int lc, int ld);

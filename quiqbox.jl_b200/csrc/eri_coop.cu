@@ -1,0 +1,395 @@
+// Warp-cooperative, table-driven ERI kernel for the LARGE shell-quartet classes.
+//
+// The thread-per-quartet kernels of eri_class.cuh keep every intermediate of a quartet in one
+// thread; from (dp|dp) upwards that is 250-1000 accumulators plus up to 2500 recurrence
+// intermediates, which spill to local memory and run at < 1 TFLOP/s.  Here one WARP owns one
+// contracted shell quartet, all intermediates live in shared memory, and the lanes share the
+// entries of every recurrence level (entries of a level are independent):
+//
+//   per primitive quartet   Boys (every lane, redundantly) -> S[m]
+//                           VRR level e -> e+1          (cf. vertTransfer,  GaussianOrbitals.jl:386)
+//                           transfer level f -> f+1     (cf. modeTransfer,  :529)
+//                           ACC += needed [e0|f0]
+//   per contracted quartet  HRR bra, HRR ket            (cf. horiTransfer,  :394), weights, store
+//
+// The recurrences are not unrolled: the host emits, per class, a "program" -- for every entry
+// the shared-memory addresses of its sources and its integer coefficients -- that the lanes
+// read coalesced.  One kernel therefore serves every class (and compiles in seconds); the
+// arithmetic is the same sequence of operations as in eri_class.cuh.
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#include "engine.h"
+
+namespace {
+
+struct Op {                     // 16 bytes, read coalesced (one 128-bit load per lane)
+    short dst, a, b, c, d;      // addresses in the warp's buffer (< 32768 doubles); -1 = absent
+    short ax, n1, n2;           // axis, integer coefficients / vector selector
+};
+static_assert(sizeof(Op) == 16, "Op layout");
+
+struct Level { int first, count; };
+
+struct Program {
+    std::vector<Op> ops;
+    std::vector<Level> vrr, xfer, hrr;      // level boundaries into ops
+    Level acc{0, 0}, store{0, 0};
+    int L = 0, buf_doubles = 0, acc_off = 0, acc_n = 0, ncomp = 0, y_off = 0;
+    int NA = 1, NB = 1, NCc = 1, ND = 1;
+    // device copies
+    Op *d_ops = nullptr;
+};
+
+int cidx(int j, int k) { return (j + k) * (j + k + 1) / 2 + k; }
+int s1(int n) { return n * (n + 1) * (n + 2) / 6; }
+int ncsum(int lo, int hi) { return s1(hi + 1) - s1(lo); }
+
+// Builds the program for class (la lb|lc ld); mirrors the loops of EriClass<...>::primitive/finish.
+Program *build_program(int LA, int LB, int LC, int LD)
+{
+    Program *P = new Program;
+    const int E = LA + LB, F = LC + LD, L = E + F;
+    P->L = L;
+    P->NA = NC(LA); P->NB = NC(LB); P->NCc = NC(LC); P->ND = NC(LD);
+    P->ncomp = P->NA * P->NB * P->NCc * P->ND;
+    auto voff = [&](int e) { return (L + 1) * s1(e) - (e - 1) * e * (e + 1) * (e + 2) / 8; };
+    const int vtot = voff(L + 1);
+    auto elo = [&](int f) { return std::max(0, LA - (F - f)); };
+    auto ehi = [&](int f) { return E + (F - f); };
+    std::vector<std::vector<int>> woff(F + 2, std::vector<int>(L + 3, -1));
+    int wtot = 0;
+    for (int f = 1; f <= F; ++f)
+        for (int e = elo(f); e <= ehi(f); ++e) { woff[f][e] = vtot + wtot; wtot += NC(f) * NC(e); }
+    auto saddr = [&](int f, int e, int ce, int cf) { return f == 0 ? voff(e) + ce : woff[f][e] + cf * NC(e) + ce; };
+    const int s_total = vtot + wtot;
+
+    // ---- VRR: level e -> e + 1, all orders m <= L - e - 1
+    for (int e = 0; e < L; ++e) {
+        Level lv{(int)P->ops.size(), 0};
+        for (int m = 0; m <= L - e - 1; ++m)
+            for (int r = 0; r <= e + 1; ++r)
+                for (int k = 0; k <= r; ++k) {
+                    const int i = e + 1 - r, j = r - k;
+                    const int ax = i > 0 ? 0 : (j > 0 ? 1 : 2);
+                    const int j1 = j - (ax == 1), k1 = k - (ax == 2), i1 = i - (ax == 0);
+                    const int n1 = ax == 0 ? i1 : (ax == 1 ? j1 : k1);
+                    Op o{};
+                    o.dst = voff(e + 1) + m * NC(e + 1) + cidx(j, k);
+                    o.a = voff(e) + m * NC(e) + cidx(j1, k1);
+                    o.b = voff(e) + (m + 1) * NC(e) + cidx(j1, k1);
+                    o.c = o.d = -1;
+                    if (n1 > 0) {
+                        const int c2 = cidx(j1 - (ax == 1), k1 - (ax == 2));
+                        o.c = voff(e - 1) + m * NC(e - 1) + c2;
+                        o.d = voff(e - 1) + (m + 1) * NC(e - 1) + c2;
+                    }
+                    o.ax = (short)ax; o.n1 = (short)n1;
+                    P->ops.push_back(o); ++lv.count;
+                }
+        P->vrr.push_back(lv);
+    }
+    // ---- electron transfer: level f -> f + 1 at m = 0
+    for (int f = 0; f < F; ++f) {
+        Level lv{(int)P->ops.size(), 0};
+        for (int rf = 0; rf <= f + 1; ++rf)
+            for (int kf = 0; kf <= rf; ++kf) {
+                const int fi = f + 1 - rf, fj = rf - kf;
+                const int ax = fi > 0 ? 0 : (fj > 0 ? 1 : 2);
+                const int fj1 = fj - (ax == 1), fk1 = kf - (ax == 2);
+                const int nf = (ax == 0 ? fi : (ax == 1 ? fj : kf)) - 1;
+                const int cf = cidx(fj, kf), cf1 = cidx(fj1, fk1);
+                for (int e = elo(f + 1); e <= ehi(f + 1); ++e)
+                    for (int re = 0; re <= e; ++re)
+                        for (int ke = 0; ke <= re; ++ke) {
+                            const int ei = e - re, ej = re - ke, ce = cidx(ej, ke);
+                            const int na = ax == 0 ? ei : (ax == 1 ? ej : ke);
+                            Op o{};
+                            o.dst = saddr(f + 1, e, ce, cf);
+                            o.a = saddr(f, e, ce, cf1);
+                            o.b = saddr(f, e + 1, cidx(ej + (ax == 1), ke + (ax == 2)), cf1);
+                            o.c = na > 0 ? saddr(f, e - 1, cidx(ej - (ax == 1), ke - (ax == 2)), cf1) : -1;
+                            o.d = nf > 0 ? saddr(f - 1, e, ce, cidx(fj1 - (ax == 1), fk1 - (ax == 2))) : -1;
+                            o.ax = (short)ax; o.n1 = (short)na; o.n2 = (short)nf;
+                            P->ops.push_back(o); ++lv.count;
+                        }
+            }
+        P->xfer.push_back(lv);
+    }
+    // ---- accumulate [e0|f0], e in [LA,E], f in [LC,F]
+    const int nae = ncsum(LA, E), nkf = ncsum(LC, F);
+    P->acc_off = s_total;
+    P->acc_n = nae * nkf;
+    auto aoff = [&](int f, int e) { return P->acc_off + (s1(f) - s1(LC)) * nae + NC(f) * (s1(e) - s1(LA)); };
+    P->acc.first = (int)P->ops.size();
+    for (int f = LC; f <= F; ++f)
+        for (int e = LA; e <= E; ++e)
+            for (int cf = 0; cf < NC(f); ++cf)
+                for (int ce = 0; ce < NC(e); ++ce) {
+                    Op o{};
+                    o.dst = aoff(f, e) + cf * NC(e) + ce;
+                    o.a = saddr(f, e, ce, cf);
+                    o.b = o.c = o.d = -1;
+                    P->ops.push_back(o); ++P->acc.count;
+                }
+    // ---- HRR: temporaries re-use the S region (dead after the primitive loop); X after ACC
+    const int x_off = P->acc_off + P->acc_n;              // X[kk][a*NB + b]
+    const int NA = P->NA, NB = P->NB, NCc = P->NCc, ND = P->ND;
+    const int y_off = x_off + nkf * NA * NB;
+    // temporaries of the two d-type HRR passes: inside the (dead) S region when they fit
+    const int need_bra = LB == 2 ? nkf * (NC(LA) + NC(LA + 1)) * 3 : 0;
+    const int need_ket = LD == 2 ? NA * NB * (NC(LC) + NC(LC + 1)) * 3 : 0;
+    const int tneed = std::max(need_bra, need_ket);
+    const int tbase = tneed <= s_total ? 0 : y_off + P->ncomp;
+    int tmp = tbase;                                      // bump allocator
+    auto hrr_pass = [&](int LX, int LY, int nouter, auto in_addr, auto out_addr, int vec, std::vector<Level> &levels) {
+        // emits up to LY levels; `vec` selects AB (0) or CD (1), encoded in n2
+        std::vector<std::vector<int>> t1(nouter);         // address of t1[o][d][c][x]
+        if (LY == 0) {
+            Level lv{(int)P->ops.size(), 0};
+            for (int o = 0; o < nouter; ++o)
+                for (int c = 0; c < NC(LX); ++c) {
+                    Op op{}; op.dst = out_addr(o, c, 0); op.a = in_addr(o, LX, c); op.b = op.c = op.d = -1; op.ax = -1; op.n2 = (short)vec;
+                    P->ops.push_back(op); ++lv.count;
+                }
+            levels.push_back(lv);
+            return;
+        }
+        Level l1{(int)P->ops.size(), 0};
+        for (int o = 0; o < nouter; ++o) {
+            t1[o].assign(LY * NC(LX + LY - 1) * 3, -1);
+            for (int d = 0; d < LY; ++d)
+                for (int r = 0; r <= LX + d; ++r)
+                    for (int k = 0; k <= r; ++k) {
+                        const int j = r - k, c = cidx(j, k);
+                        for (int x = 0; x < 3; ++x) {
+                            Op op{};
+                            const bool final1 = (LY == 1);
+                            op.dst = final1 ? out_addr(o, c, x) : (t1[o][(d * NC(LX + LY - 1) + c) * 3 + x] = tmp++);
+                            op.a = in_addr(o, LX + d + 1, cidx(j + (x == 1), k + (x == 2)));     // hi
+                            op.b = in_addr(o, LX + d, c);                                       // lo
+                            op.c = op.d = -1; op.ax = (short)x; op.n2 = (short)vec;
+                            P->ops.push_back(op); ++l1.count;
+                        }
+                    }
+        }
+        levels.push_back(l1);
+        if (LY == 2) {
+            Level l2{(int)P->ops.size(), 0};
+            static const int dax[6] = {0, 0, 0, 1, 1, 2}, drem[6] = {0, 1, 2, 1, 2, 2};   // xx xy xz yy yz zz
+            for (int o = 0; o < nouter; ++o)
+                for (int r = 0; r <= LX; ++r)
+                    for (int k = 0; k <= r; ++k) {
+                        const int j = r - k, c = cidx(j, k);
+                        for (int b = 0; b < 6; ++b) {
+                            const int ax = dax[b], rem = drem[b];
+                            Op op{};
+                            op.dst = out_addr(o, c, b);
+                            op.a = t1[o][(1 * NC(LX + 1) + cidx(j + (ax == 1), k + (ax == 2))) * 3 + rem];
+                            op.b = t1[o][(0 * NC(LX + 1) + c) * 3 + rem];
+                            op.c = op.d = -1; op.ax = (short)ax; op.n2 = (short)vec;
+                            P->ops.push_back(op); ++l2.count;
+                        }
+                    }
+            levels.push_back(l2);
+        }
+    };
+    // bra: outer index = stacked ket component kk; input ACC[(f,cf)][e][ce]
+    std::vector<int> kk_f(nkf), kk_cf(nkf);
+    { int kk = 0; for (int f = LC; f <= F; ++f) for (int cf = 0; cf < NC(f); ++cf) { kk_f[kk] = f; kk_cf[kk] = cf; ++kk; } }
+    hrr_pass(LA, LB, nkf,
+             [&](int kk, int e, int c) { return aoff(kk_f[kk], e) + kk_cf[kk] * NC(e) + c; },
+             [&](int kk, int a, int b) { return x_off + kk * NA * NB + a * NB + b; }, 0, P->hrr);
+    // ket: outer index = ab; input X[(f,c)][ab]; output goes to the Y region (then stored)
+    tmp = tbase;                                          // bra temporaries are dead once X is complete
+    hrr_pass(LC, LD, NA * NB,
+             [&](int ab, int f, int c) { return x_off + (ncsum(LC, f - 1) + c) * NA * NB + ab; },
+             [&](int ab, int c, int d) { return y_off + (ab * NCc + c) * ND + d; }, 1, P->hrr);
+    P->y_off = y_off;
+    P->buf_doubles = y_off + P->ncomp + (tbase ? tneed : 0);
+    if (P->buf_doubles >= 32768) { delete P; return nullptr; }
+    return P;
+}
+
+struct CoopArgs {
+    PairSet bra, ket;
+    const int2 *tasks;
+    int64_t ntasks;
+    double *out;
+    const double *shell_scale;
+    BoysTable boys;
+    const Op *ops;
+    int L, buf, acc_off, acc_n, y_off, ncomp, NA, NB, NCc, ND;
+    int nvrr, nxfer, nhrr;
+    Level vrr[9], xfer[5], hrr[4], acc;
+};
+
+__device__ __forceinline__ void boys_rt(const BoysTable &tb, double T, double scale, int L, double *F)
+{
+    const bool big = T >= QBX_BOYS_TMAX;
+    const int i = big ? (QBX_BOYS_NROW - 2) : __double2int_rn(T * QBX_BOYS_STEP_INV);
+    const double *row = tb.f + i * QBX_BOYS_NCOL + L;
+    const double mx = fma((double)i, 1.0 / QBX_BOYS_STEP_INV, -T);
+    double r = __ldg(row + 7);
+    r = fma(r, mx * (1.0 / 7.0), __ldg(row + 6));
+    r = fma(r, mx * (1.0 / 6.0), __ldg(row + 5));
+    r = fma(r, mx * (1.0 / 5.0), __ldg(row + 4));
+    r = fma(r, mx * (1.0 / 4.0), __ldg(row + 3));
+    r = fma(r, mx * (1.0 / 3.0), __ldg(row + 2));
+    r = fma(r, mx * (1.0 / 2.0), __ldg(row + 1));
+    r = fma(r, mx, __ldg(row));
+    double ex = 1.0 / 5040.0;
+    ex = fma(ex, mx, 1.0 / 720.0);
+    ex = fma(ex, mx, 1.0 / 120.0);
+    ex = fma(ex, mx, 1.0 / 24.0);
+    ex = fma(ex, mx, 1.0 / 6.0);
+    ex = fma(ex, mx, 0.5);
+    ex = fma(ex, mx, 1.0);
+    ex = fma(ex, mx, 1.0);
+    ex *= __ldg(tb.e + i);
+    const double rt = rsqrt(T), h = 0.5 * rt * rt;
+    double as = 0.88622692545275801365 * rt;
+    for (int m = 0; m < L; ++m) as *= (2.0 * m + 1.0) * h;
+    double f = (big ? as : r) * scale;
+    ex = big ? 0.0 : ex * scale;
+    F[L] = f;
+    const double t2 = 2.0 * T;
+    for (int m = L; m >= 1; --m) { f = fma(t2, f, ex) * (1.0 / (2.0 * m - 1.0)); F[m - 1] = f; }
+}
+
+#define COOP_WARPS 4
+
+__global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *B = smem + (size_t)wib * p.buf;
+    const int64_t warp0 = (int64_t)blockIdx.x * COOP_WARPS + wib, nwarps = (int64_t)gridDim.x * COOP_WARPS;
+    for (int64_t q = warp0; q < p.ntasks; q += nwarps) {
+        const int2 t = p.tasks[q];
+        const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
+        const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
+        const double CD[3] = {gk[3], gk[4], gk[5]};
+        const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
+        const int pk0 = p.ket.prim_off[t.y], pk1 = p.ket.prim_off[t.y + 1];
+        for (int i = lane; i < p.acc_n; i += 32) B[p.acc_off + i] = 0.0;
+        for (int pb = pb0; pb < pb1; ++pb) {
+            const double *rb = p.bra.prim + 8 * (int64_t)pb;
+            const double zeta = __ldg(rb), P[3] = {__ldg(rb + 1), __ldg(rb + 2), __ldg(rb + 3)};
+            const double Kab = __ldg(rb + 4), bx = __ldg(rb + 5), i2z = __ldg(rb + 6);
+            const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+            for (int pk = pk0; pk < pk1; ++pk) {
+                const double *rk = p.ket.prim + 8 * (int64_t)pk;
+                const double eta = __ldg(rk), Q[3] = {__ldg(rk + 1), __ldg(rk + 2), __ldg(rk + 3)};
+                const double Kcd = __ldg(rk + 4), dx = __ldg(rk + 5), i2e = __ldg(rk + 6);
+                const double rs = rsqrt(zeta + eta), inv = rs * rs, rz = eta * inv;
+                const double PQ[3] = {P[0] - Q[0], P[1] - Q[1], P[2] - Q[2]};
+                const double T = zeta * rz * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+                const double WP[3] = {-rz * PQ[0], -rz * PQ[1], -rz * PQ[2]};
+                const double ie = 2.0 * i2e, zoe = zeta * ie;
+                const double k0[3] = {-(bx * AB[0] + dx * CD[0]) * ie, -(bx * AB[1] + dx * CD[1]) * ie,
+                                      -(bx * AB[2] + dx * CD[2]) * ie};
+                double Fm[9];
+                boys_rt(p.boys, T, Kab * Kcd * rs, p.L, Fm);
+                __syncwarp();                              // previous accumulate has read S
+                if (lane <= p.L) B[lane] = Fm[lane];
+                __syncwarp();
+                for (int lv = 0; lv < p.nvrr; ++lv) {
+                    const Op *ops = p.ops + p.vrr[lv].first;
+                    for (int i = lane; i < p.vrr[lv].count; i += 32) {
+                        const Op o = ops[i];
+                        double v = fma(PA[o.ax], B[o.a], WP[o.ax] * B[o.b]);
+                        if (o.c >= 0) v = fma(o.n1 * i2z, fma(-rz, B[o.d], B[o.c]), v);
+                        B[o.dst] = v;
+                    }
+                    __syncwarp();
+                }
+                for (int lv = 0; lv < p.nxfer; ++lv) {
+                    const Op *ops = p.ops + p.xfer[lv].first;
+                    for (int i = lane; i < p.xfer[lv].count; i += 32) {
+                        const Op o = ops[i];
+                        double v = fma(k0[o.ax], B[o.a], -zoe * B[o.b]);
+                        if (o.c >= 0) v = fma(o.n1 * i2e, B[o.c], v);
+                        if (o.d >= 0) v = fma(o.n2 * i2e, B[o.d], v);
+                        B[o.dst] = v;
+                    }
+                    __syncwarp();
+                }
+                {
+                    const Op *ops = p.ops + p.acc.first;
+                    for (int i = lane; i < p.acc.count; i += 32) {
+                        const Op o = ops[i];
+                        B[o.dst] += B[o.a];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        for (int lv = 0; lv < p.nhrr; ++lv) {
+            const Op *ops = p.ops + p.hrr[lv].first;
+            for (int i = lane; i < p.hrr[lv].count; i += 32) {
+                const Op o = ops[i];
+                double v = B[o.a];
+                if (o.ax >= 0) v = fma(o.n2 ? CD[o.ax] : AB[o.ax], B[o.b], v);
+                B[o.dst] = v;
+            }
+            __syncwarp();
+        }
+        const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
+        const double *sA = p.shell_scale + 6 * sb.x, *sB = p.shell_scale + 6 * sb.y;
+        const double *sC = p.shell_scale + 6 * sk.x, *sD = p.shell_scale + 6 * sk.y;
+        for (int c = lane; c < p.ncomp; c += 32) {
+            const int d = c % p.ND, cc = (c / p.ND) % p.NCc, b = (c / (p.ND * p.NCc)) % p.NB, a = c / (p.ND * p.NCc * p.NB);
+            p.out[(int64_t)c * p.ntasks + q] = B[p.y_off + c] * sA[a] * sB[b] * sC[cc] * sD[d];
+        }
+        __syncwarp();
+    }
+}
+
+std::map<int, Program *> g_programs;
+
+}  // namespace
+
+// Returns QBX_OK after launching, or -1 if this class is not served by the cooperative kernel.
+int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cudaStream_t s)
+{
+    const int key = la * 1000 + lb * 100 + lc * 10 + ld;
+    auto it = g_programs.find(key);
+    if (it == g_programs.end()) {
+        Program *P = build_program(la, lb, lc, ld);
+        if (!P) return -1;
+        QBX_CUDA(cudaMalloc(&P->d_ops, P->ops.size() * sizeof(Op)));
+        QBX_CUDA(cudaMemcpy(P->d_ops, P->ops.data(), P->ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
+        it = g_programs.emplace(key, P).first;
+    }
+    Program *P = it->second;
+    if (a.ntasks <= 0) return QBX_OK;
+    CoopArgs c{};
+    c.bra = a.bra; c.ket = a.ket; c.tasks = a.tasks; c.ntasks = a.ntasks; c.out = a.out;
+    c.shell_scale = a.shell_scale; c.boys = a.boys; c.ops = P->d_ops;
+    c.L = P->L; c.buf = P->buf_doubles; c.acc_off = P->acc_off; c.acc_n = P->acc_n;
+    c.ncomp = P->ncomp; c.y_off = P->y_off;
+    c.NA = P->NA; c.NB = P->NB; c.NCc = P->NCc; c.ND = P->ND;
+    c.nvrr = (int)P->vrr.size(); c.nxfer = (int)P->xfer.size(); c.nhrr = (int)P->hrr.size();
+    for (int i = 0; i < c.nvrr; ++i) c.vrr[i] = P->vrr[i];
+    for (int i = 0; i < c.nxfer; ++i) c.xfer[i] = P->xfer[i];
+    for (int i = 0; i < c.nhrr; ++i) c.hrr[i] = P->hrr[i];
+    c.acc = P->acc;
+    const size_t smem = (size_t)COOP_WARPS * P->buf_doubles * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        QBX_CUDA(cudaFuncSetAttribute(eri_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    if (smem > 227 * 1024) { qbx_set_error("internal: cooperative ERI kernel buffer exceeds shared memory"); return QBX_ERR_STATE; }
+    int dev = 0, sms = 0, per_sm = 0;
+    QBX_CUDA(cudaGetDevice(&dev));
+    QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_coop_kernel, COOP_WARPS * 32, smem));
+    const int64_t need = (a.ntasks + COOP_WARPS - 1) / COOP_WARPS;
+    const int64_t cap = (int64_t)sms * std::max(per_sm, 1);
+    eri_coop_kernel<<<(unsigned)std::min(need, cap), COOP_WARPS * 32, smem, s>>>(c);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}

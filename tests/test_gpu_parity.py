@@ -263,3 +263,27 @@ def test_boundary_errors():
     assert L.load().qbx_fock_build(db.handle, 1, L.ptr(D), L.ptr(D), L.ptr(G)) != 0  # nothing stored yet
     with pytest.raises(L.QbxError):
         qb.DeviceERI(db, mode="dense", nranks=2, rank=0)
+
+
+# ------------------------------------------------------------------ warp-cooperative kernel on every class
+def test_cooperative_kernel_all_classes_vs_oracle():
+    """QBX_COOP_MIN_ACC=0 routes EVERY s/p/d class through eri_coop.cu (normally only the large
+    ones); the full H2O/cc-pVDZ tensor must still match the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path[:0] = [%r, %r]
+import oracle, quiqbox_b200 as qb
+from molecules import h2o
+nuc, xyz = h2o()
+bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+T = qb.elecRepulsions(bs)
+ref = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs)).eri_tensor()
+err = float(np.max(np.abs(T - ref)))
+print("ERR", err)
+assert err < 1e-12
+''' % (os.path.dirname(HERE), HERE)
+    env = dict(os.environ, QBX_COOP_MIN_ACC="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
