@@ -116,6 +116,7 @@ __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk
 }
 
 #define QBX_TASK_CHUNK 4096
+#define QBX_SEG_MAX 2048
 // one warp per bra row: compact the surviving kets in order; keep the chunks of this rank
 __global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol,
                              const int64_t *rowoff, int rank, int nranks, int2 *tasks)
@@ -162,6 +163,30 @@ __global__ void k_finish_G(int64_t N, int nmat, const double *Jt, const double *
     const int64_t i = e % N, j = e / N, et = j + N * i;
     const double jv = Jt[e] + Jt[et];
     for (int m = 0; m < nmat; ++m) G[m * N * N + e] = jv - (Kt[m * N * N + e] + Kt[m * N * N + et]);
+}
+
+// DJ as a pair vector: dpair[comp][pair] = DJ[f_X(a), f_Y(b)]; and the reverse scatter of J
+__global__ void k_pair_gather(const int2 *shells, int npair, int nb, int ncomp, const int *shell_bf, int64_t N,
+                              const double *DJ, double *dpair, double *jpair)
+{
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)npair * ncomp) return;
+    const int pair = (int)(idx % npair), comp = (int)(idx / npair);
+    const int2 sh = shells[pair];
+    const int fa = shell_bf[6 * sh.x + comp / nb], fb = shell_bf[6 * sh.y + comp % nb];
+    dpair[idx] = (fa >= 0 && fb >= 0) ? DJ[fa + N * fb] : 0.0;
+    jpair[idx] = 0.0;
+}
+__global__ void k_pair_scatter(const int2 *shells, int npair, int nb, int ncomp, const int *shell_bf, int64_t N,
+                               const double *jpair, double *Jt)
+{
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)npair * ncomp) return;
+    const int pair = (int)(idx % npair), comp = (int)(idx / npair);
+    const int2 sh = shells[pair];
+    const int fa = shell_bf[6 * sh.x + comp / nb], fb = shell_bf[6 * sh.y + comp % nb];
+    const double v = jpair[idx];
+    if (fa >= 0 && fb >= 0 && v != 0.0) atomicAdd(Jt + fa + N * fb, v);
 }
 
 __global__ void k_sum(const double *v, int64_t n, double *sum)
@@ -371,6 +396,8 @@ Engine::~Engine()
     for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
+    for (auto &p : d_dpair_) cudaFree(p);
+    for (auto &p : d_jpair_) cudaFree(p);
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -380,7 +407,7 @@ void Engine::release_store()
 {
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
-            cudaFree(tasks_[b][k].tasks); tasks_[b][k] = TaskList();
+            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].segs); tasks_[b][k] = TaskList();
             cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
         }
     mode_ = -1;
@@ -477,6 +504,29 @@ int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskLi
     k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol,
                                                                    d_off, rank, nranks, out.tasks);
     QBX_CUDA(cudaGetLastError());
+    // bra-uniform segments of this rank's list (row-block digestion): a row's global range is
+    // cut at the rank's chunks and then into pieces of at most QBX_SEG_MAX tasks
+    {
+        std::vector<int2> segs;
+        for (int i = 0; i < B.npair; ++i) {
+            for (int64_t g = rowoff[i]; g < rowoff[i + 1];) {
+                const int64_t c = g / QBX_TASK_CHUNK, gend = std::min<int64_t>(rowoff[i + 1], (c + 1) * QBX_TASK_CHUNK);
+                if (c % nranks == rank) {
+                    int64_t loc = (c / nranks) * QBX_TASK_CHUNK + g % QBX_TASK_CHUNK, left = gend - g;
+                    while (left > 0) {
+                        const int64_t n = std::min<int64_t>(left, QBX_SEG_MAX);
+                        segs.push_back(make_int2((int)loc, (int)n));
+                        loc += n; left -= n;
+                    }
+                }
+                g = gend;
+            }
+        }
+        out.nsegs = (int)segs.size();
+        QBX_CUDA(cudaMalloc(&out.segs, std::max<size_t>(1, segs.size()) * sizeof(int2)));
+        if (!segs.empty()) QBX_CUDA(cudaMemcpyAsync(out.segs, segs.data(), segs.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaStreamSynchronize(s));
+    }
     double *d_sum = nullptr;
     QBX_CUDA(cudaMalloc(&d_sum, sizeof(double)));
     QBX_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), s));
@@ -510,7 +560,7 @@ int Engine::fill_tensor(double *d_tensor, cudaStream_t s, double *stats)
             }
             stats[3] += tl.nprimq;
             QBX_CUDA(cudaStreamSynchronize(s));
-            cudaFree(tl.tasks);
+            cudaFree(tl.tasks); cudaFree(tl.segs);
         }
     return QBX_OK;
 }
@@ -544,6 +594,11 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
     if (!d_Jt_) {
         QBX_CUDA(cudaMalloc(&d_Jt_, nbf_ * nbf_ * sizeof(double)));
         QBX_CUDA(cudaMalloc(&d_Kt_, 2 * nbf_ * nbf_ * sizeof(double)));
+        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+            const size_t n = std::max<size_t>(1, (size_t)pairs_[pc].npair * qbx_nc(pairs_[pc].la) * qbx_nc(pairs_[pc].lb));
+            QBX_CUDA(cudaMalloc(&d_dpair_[pc], n * sizeof(double)));
+            QBX_CUDA(cudaMalloc(&d_jpair_[pc], n * sizeof(double)));
+        }
     }
     mode_ = mode;
     if (mode == 0) {
@@ -607,11 +662,37 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
     const int64_t N2 = nbf_ * nbf_;
     QBX_CUDA(cudaMemsetAsync(d_Jt_, 0, N2 * sizeof(double), s));
     QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * N2 * sizeof(double), s));
+    if (mode_ == 0)
+        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+            const DevPairSet &P = pairs_[pc];
+            const int ncomp = qbx_nc(P.la) * qbx_nc(P.lb);
+            if (P.npair == 0) continue;
+            k_pair_gather<<<(unsigned)(((int64_t)P.npair * ncomp + 255) / 256), 256, 0, s>>>(
+                P.shells, P.npair, qbx_nc(P.lb), ncomp, d_shell_bf_, nbf_, dDJ, d_dpair_[pc], d_jpair_[pc]);
+            stats[0] += 1;
+        }
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc) {
             const TaskList &tl = tasks_[bc][kc];
             if (tl.n == 0) continue;
             const ClassOps *ops = qbx_class_ops(bc, kc);
+            if (mode_ == 0) {
+                Digest2Args d;
+                d.bra_shells = pairs_[bc].shells; d.ket_shells = pairs_[kc].shells;
+                d.tasks = tl.tasks; d.ntasks = tl.n; d.vals = vals_[bc][kc];
+                d.shell_bf = d_shell_bf_; d.nbf = (int)nbf_; d.nmat = nmat; d.same_class = (bc == kc);
+                d.DK = dDK; d.Kt = d_Kt_;
+                d.dbra = d_dpair_[bc]; d.dket = d_dpair_[kc]; d.jbra = d_jpair_[bc]; d.jket = d_jpair_[kc];
+                d.nbra = pairs_[bc].npair; d.nket = pairs_[kc].npair;
+                d.segs = tl.segs; d.nsegs = tl.nsegs;
+                const int rc2 = ops->digest2(d, s);
+                if (rc2 > 0) return rc2;
+                if (rc2 == 0) {
+                    stats[0] += 1;
+                    stats[5] += (double)tl.n * ops->ncomp * sizeof(double) * nmat;
+                    continue;
+                }
+            }
             DigestArgs a;
             a.bra_shells = pairs_[bc].shells; a.ket_shells = pairs_[kc].shells;
             a.shell_bf = d_shell_bf_; a.nbf = (int)nbf_; a.nmat = nmat; a.same_class = (bc == kc);
@@ -636,6 +717,15 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             }
         }
     if (mode_ == 1) stats[4] += model_flops_;
+    if (mode_ == 0)
+        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+            const DevPairSet &P = pairs_[pc];
+            const int ncomp = qbx_nc(P.la) * qbx_nc(P.lb);
+            if (P.npair == 0) continue;
+            k_pair_scatter<<<(unsigned)(((int64_t)P.npair * ncomp + 255) / 256), 256, 0, s>>>(
+                P.shells, P.npair, qbx_nc(P.lb), ncomp, d_shell_bf_, nbf_, d_jpair_[pc], d_Jt_);
+            stats[0] += 1;
+        }
     k_finish_G<<<(unsigned)((N2 + 255) / 256), 256, 0, s>>>(nbf_, nmat, d_Jt_, d_Kt_, dG);
     QBX_CUDA(cudaGetLastError());
     stats[0] += 1;
