@@ -20,9 +20,6 @@ FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
-# NVVM's -O3 pipeline needs > 30 min on the fully unrolled (dd|dp) ERI kernel (every other
-# class finishes in seconds to ~5 min); that class (0.1 % of the (H2O)16 work) is built at -O1.
-SLOW_TO_OPTIMISE = {(2, 2, 2, 1)}
 HEADERS = ["boys.cuh", "qbx_internal.h", "eri_class.cuh", "digest.cuh", "engine.h", "../../include/qbx.h"]
 
 
@@ -55,10 +52,7 @@ def build(jobs=None, force=False, verbose=True):
         obj = os.path.join(OBJ, f"class_{a}{b}{c}{d}.o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
-            defs = [f"-DQLA={a}", f"-DQLB={b}", f"-DQLC={c}", f"-DQLD={d}"]
-            if (a, b, c, d) in SLOW_TO_OPTIMISE:
-                defs += ["-Xcicc", "-O1"]
-            work.append((src, obj, defs))
+            work.append((src, obj, [f"-DQLA={a}", f"-DQLB={b}", f"-DQLC={c}", f"-DQLD={d}"]))
     if work:
         with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
             for obj, rc, out in ex.map(_compile, work):

@@ -5,8 +5,16 @@
 #define QBX_CAT2(a, b, c, d) qbx_ops_##a##b##c##d
 #define QBX_CAT(a, b, c, d) QBX_CAT2(a, b, c, d)
 
+// Classes with >= QBX_COOP_ACC contracted accumulators per quartet are served by the
+// warp-cooperative kernel (eri_coop.cu) only: the thread-per-quartet kernel is not instantiated
+// for them (it spills, and NVVM needs minutes to tens of minutes to optimise it).
 static int launch_eri(const ClassArgs &a, cudaStream_t s)
 {
+    if constexpr (NCSUM(QLA, QLA + QLB) * NCSUM(QLC, QLC + QLD) >= QBX_COOP_ACC) {
+        (void)a; (void)s;
+        qbx_set_error("internal: this class is served by the cooperative kernel");
+        return QBX_ERR_STATE;
+    } else {
     if (a.ntasks <= 0) return QBX_OK;
     static int max_blocks = 0;           // resident blocks on the whole device for this kernel
     if (max_blocks == 0) {
@@ -22,6 +30,7 @@ static int launch_eri(const ClassArgs &a, cudaStream_t s)
     eri_class_kernel<QLA, QLB, QLC, QLD><<<grid, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
+    }
 }
 static int launch_digest(const DigestArgs &a, cudaStream_t s)
 {
@@ -29,32 +38,6 @@ static int launch_digest(const DigestArgs &a, cudaStream_t s)
     digest_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
-}
-template <int W>
-static int launch_digest2_w(const Digest2Args &a, cudaStream_t s, size_t smem)
-{
-    static bool attr = false;
-    if (!attr) {
-        QBX_CUDA(cudaFuncSetAttribute(digest2_kernel<QLA, QLB, QLC, QLD, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
-    int dev = 0, sms = 0, per_sm = 0;
-    QBX_CUDA(cudaGetDevice(&dev));
-    QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, digest2_kernel<QLA, QLB, QLC, QLD, W>, W * 32, smem));
-    const int cap = sms * (per_sm > 0 ? per_sm : 1);
-    digest2_kernel<QLA, QLB, QLC, QLD, W><<<a.nsegs < cap ? a.nsegs : cap, W * 32, smem, s>>>(a);
-    QBX_CUDA(cudaGetLastError());
-    return QBX_OK;
-}
-static int launch_digest2(const Digest2Args &a, cudaStream_t s)
-{
-    if (a.nsegs <= 0) return QBX_OK;
-    constexpr int NR = NC(QLA) + NC(QLB);
-    const size_t row = (size_t)NR * a.nbf * sizeof(double);
-    if (9 * row <= 100 * 1024) return launch_digest2_w<8>(a, s, 9 * row);     // >= 2 blocks per SM
-    if (5 * row <= 200 * 1024) return launch_digest2_w<4>(a, s, 5 * row);
-    return -1;                                                                // rows too long: digest_kernel
 }
 static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 {
@@ -67,4 +50,4 @@ static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 extern const ClassOps QBX_CAT(QLA, QLB, QLC, QLD);
 const ClassOps QBX_CAT(QLA, QLB, QLC, QLD) = {QLA, QLB, QLC, QLD,
                                               EriClass<QLA, QLB, QLC, QLD>::NCOMP,
-                                              launch_eri, launch_digest, launch_digest2, launch_scatter};
+                                              launch_eri, launch_digest, launch_scatter};

@@ -116,7 +116,6 @@ __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk
 }
 
 #define QBX_TASK_CHUNK 4096
-#define QBX_SEG_MAX 2048
 // one warp per bra row: compact the surviving kets in order; keep the chunks of this rank
 __global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol,
                              const int64_t *rowoff, int rank, int nranks, int2 *tasks)
@@ -156,37 +155,27 @@ __global__ void k_task_cost(const int2 *tasks, int64_t n, const int *poffb, cons
     if (threadIdx.x == 0) atomicAdd(sum, red[0]);
 }
 
-__global__ void k_finish_G(int64_t N, int nmat, const double *Jt, const double *Kt, double *G)
+// G = (Jt + Jt^T) - (Kt + Kt^T), written in the caller's (external) numbering
+__global__ void k_finish_G(int64_t Nint, int64_t Next, const int *ext_of_int, int nmat, const double *Jt, const double *Kt,
+                           double *G)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= N * N) return;
-    const int64_t i = e % N, j = e / N, et = j + N * i;
+    if (e >= Nint * Nint) return;
+    const int64_t i = e % Nint, j = e / Nint, et = j + Nint * i;
+    const int ie = ext_of_int[i], je = ext_of_int[j];
+    if (ie < 0 || je < 0) return;
     const double jv = Jt[e] + Jt[et];
-    for (int m = 0; m < nmat; ++m) G[m * N * N + e] = jv - (Kt[m * N * N + e] + Kt[m * N * N + et]);
+    for (int m = 0; m < nmat; ++m)
+        G[m * Next * Next + ie + Next * je] = jv - (Kt[m * Nint * Nint + e] + Kt[m * Nint * Nint + et]);
 }
 
-// DJ as a pair vector: dpair[comp][pair] = DJ[f_X(a), f_Y(b)]; and the reverse scatter of J
-__global__ void k_pair_gather(const int2 *shells, int npair, int nb, int ncomp, const int *shell_bf, int64_t N,
-                              const double *DJ, double *dpair, double *jpair)
+// external <-> internal function numbering (internal = complete Cartesian shells, shell by shell)
+__global__ void k_permute_in(int64_t Next, int64_t Nint, const int *ext_of_int, const double *Dext, double *Dint)
 {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)npair * ncomp) return;
-    const int pair = (int)(idx % npair), comp = (int)(idx / npair);
-    const int2 sh = shells[pair];
-    const int fa = shell_bf[6 * sh.x + comp / nb], fb = shell_bf[6 * sh.y + comp % nb];
-    dpair[idx] = (fa >= 0 && fb >= 0) ? DJ[fa + N * fb] : 0.0;
-    jpair[idx] = 0.0;
-}
-__global__ void k_pair_scatter(const int2 *shells, int npair, int nb, int ncomp, const int *shell_bf, int64_t N,
-                               const double *jpair, double *Jt)
-{
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)npair * ncomp) return;
-    const int pair = (int)(idx % npair), comp = (int)(idx / npair);
-    const int2 sh = shells[pair];
-    const int fa = shell_bf[6 * sh.x + comp / nb], fb = shell_bf[6 * sh.y + comp % nb];
-    const double v = jpair[idx];
-    if (fa >= 0 && fb >= 0 && v != 0.0) atomicAdd(Jt + fa + N * fb, v);
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= Nint * Nint) return;
+    const int i = ext_of_int[e % Nint], j = ext_of_int[e / Nint];
+    Dint[e] = (i >= 0 && j >= 0) ? Dext[i + Next * j] : 0.0;
 }
 
 __global__ void k_sum(const double *v, int64_t n, double *sum)
@@ -266,7 +255,11 @@ Engine *Engine::create(int64_t nprim, const double *cen, const double *xpn, cons
         shells[found].bf[comp] = (int)f;
         shells[found].scale[comp] = ratio;
     }
-    std::stable_sort(shells.begin(), shells.end(), [](const HostShell &a, const HostShell &b) { return a.l < b.l; });
+    // internal order: by l, then longer contractions first (so that, for a fixed first shell, the
+    // pairs (C,D) listed with D ascending have non-increasing primitive counts), then input order
+    std::stable_sort(shells.begin(), shells.end(), [](const HostShell &a, const HostShell &b) {
+        return a.l != b.l ? a.l < b.l : a.xpn.size() > b.xpn.size();
+    });
     return from_shells(shells, nbf, false);
 }
 
@@ -370,6 +363,16 @@ int Engine::upload(bool pair_adjacent)
     QBX_CUDA(cudaMalloc(&d_shell_scale_, std::max<size_t>(1, sc.size()) * sizeof(double)));
     QBX_CUDA(cudaMemcpy(d_shell_bf_, bf.data(), bf.size() * sizeof(int), cudaMemcpyHostToDevice));
     QBX_CUDA(cudaMemcpy(d_shell_scale_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<int> first(ns), ext;
+    for (size_t s = 0; s < ns; ++s) {
+        first[s] = (int)ext.size();
+        for (int c = 0; c < qbx_nc(shells_[s].l); ++c) ext.push_back(shells_[s].bf[c]);
+    }
+    nint_ = (int64_t)ext.size();
+    QBX_CUDA(cudaMalloc(&d_shell_first_, std::max<size_t>(1, ns) * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&d_ext_of_int_, std::max<size_t>(1, ext.size()) * sizeof(int)));
+    QBX_CUDA(cudaMemcpy(d_shell_first_, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice));
+    QBX_CUDA(cudaMemcpy(d_ext_of_int_, ext.data(), ext.size() * sizeof(int), cudaMemcpyHostToDevice));
     std::vector<std::pair<int, int>> sp[QBX_NPAIRCLS];
     if (pair_adjacent) {
         for (size_t s = 0; s + 1 < ns; s += 2) {
@@ -382,7 +385,7 @@ int Engine::upload(bool pair_adjacent)
             for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
     }
     for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc]);
+        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], false, pairs_[pc]);   // keep (A major, B ascending)
         if (rc) return rc;
     }
     QBX_CUDA(cudaEventCreate(&ev0_));
@@ -394,10 +397,9 @@ Engine::~Engine()
 {
     release_store();
     for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); }
-    cudaFree(d_shell_bf_); cudaFree(d_shell_scale_);
+    cudaFree(d_shell_bf_); cudaFree(d_shell_scale_); cudaFree(d_shell_first_); cudaFree(d_ext_of_int_); cudaFree(d_Dint_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
-    for (auto &p : d_dpair_) cudaFree(p);
-    for (auto &p : d_jpair_) cudaFree(p);
+
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -407,7 +409,7 @@ void Engine::release_store()
 {
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
-            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].segs); tasks_[b][k] = TaskList();
+            cudaFree(tasks_[b][k].tasks); tasks_[b][k] = TaskList();
             cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
         }
     mode_ = -1;
@@ -442,7 +444,7 @@ int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, c
     a.boys = qbx_boys_table();
     // Large classes (>= coop_min contracted accumulators per quartet) go to the warp-cooperative
     // kernel; QBX_COOP_MIN_ACC overrides the threshold (0 = every class, for tests).
-    static const int coop_min = getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : 180;
+    static const int coop_min = std::min(QBX_COOP_ACC, getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : QBX_COOP_ACC);
     const int nacc = NCSUM(ops->la, ops->la + ops->lb) * NCSUM(ops->lc, ops->lc + ops->ld);
     if (nacc >= coop_min) {
         const int rc = qbx_launch_eri_coop(ops->la, ops->lb, ops->lc, ops->ld, a, s);
@@ -504,29 +506,6 @@ int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskLi
     k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol,
                                                                    d_off, rank, nranks, out.tasks);
     QBX_CUDA(cudaGetLastError());
-    // bra-uniform segments of this rank's list (row-block digestion): a row's global range is
-    // cut at the rank's chunks and then into pieces of at most QBX_SEG_MAX tasks
-    {
-        std::vector<int2> segs;
-        for (int i = 0; i < B.npair; ++i) {
-            for (int64_t g = rowoff[i]; g < rowoff[i + 1];) {
-                const int64_t c = g / QBX_TASK_CHUNK, gend = std::min<int64_t>(rowoff[i + 1], (c + 1) * QBX_TASK_CHUNK);
-                if (c % nranks == rank) {
-                    int64_t loc = (c / nranks) * QBX_TASK_CHUNK + g % QBX_TASK_CHUNK, left = gend - g;
-                    while (left > 0) {
-                        const int64_t n = std::min<int64_t>(left, QBX_SEG_MAX);
-                        segs.push_back(make_int2((int)loc, (int)n));
-                        loc += n; left -= n;
-                    }
-                }
-                g = gend;
-            }
-        }
-        out.nsegs = (int)segs.size();
-        QBX_CUDA(cudaMalloc(&out.segs, std::max<size_t>(1, segs.size()) * sizeof(int2)));
-        if (!segs.empty()) QBX_CUDA(cudaMemcpyAsync(out.segs, segs.data(), segs.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-        QBX_CUDA(cudaStreamSynchronize(s));
-    }
     double *d_sum = nullptr;
     QBX_CUDA(cudaMalloc(&d_sum, sizeof(double)));
     QBX_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), s));
@@ -560,7 +539,7 @@ int Engine::fill_tensor(double *d_tensor, cudaStream_t s, double *stats)
             }
             stats[3] += tl.nprimq;
             QBX_CUDA(cudaStreamSynchronize(s));
-            cudaFree(tl.tasks); cudaFree(tl.segs);
+            cudaFree(tl.tasks);
         }
     return QBX_OK;
 }
@@ -592,13 +571,9 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
             }
         }
     if (!d_Jt_) {
-        QBX_CUDA(cudaMalloc(&d_Jt_, nbf_ * nbf_ * sizeof(double)));
-        QBX_CUDA(cudaMalloc(&d_Kt_, 2 * nbf_ * nbf_ * sizeof(double)));
-        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-            const size_t n = std::max<size_t>(1, (size_t)pairs_[pc].npair * qbx_nc(pairs_[pc].la) * qbx_nc(pairs_[pc].lb));
-            QBX_CUDA(cudaMalloc(&d_dpair_[pc], n * sizeof(double)));
-            QBX_CUDA(cudaMalloc(&d_jpair_[pc], n * sizeof(double)));
-        }
+        QBX_CUDA(cudaMalloc(&d_Jt_, nint_ * nint_ * sizeof(double)));
+        QBX_CUDA(cudaMalloc(&d_Kt_, 2 * nint_ * nint_ * sizeof(double)));
+        QBX_CUDA(cudaMalloc(&d_Dint_, 3 * nint_ * nint_ * sizeof(double)));
     }
     mode_ = mode;
     if (mode == 0) {
@@ -659,44 +634,25 @@ int Engine::class_stats(double *out)
 int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats)
 {
     if (mode_ != 0 && mode_ != 1) { qbx_set_error("fock: no ERI representation stored"); return QBX_ERR_STATE; }
-    const int64_t N2 = nbf_ * nbf_;
-    QBX_CUDA(cudaMemsetAsync(d_Jt_, 0, N2 * sizeof(double), s));
-    QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * N2 * sizeof(double), s));
-    if (mode_ == 0)
-        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-            const DevPairSet &P = pairs_[pc];
-            const int ncomp = qbx_nc(P.la) * qbx_nc(P.lb);
-            if (P.npair == 0) continue;
-            k_pair_gather<<<(unsigned)(((int64_t)P.npair * ncomp + 255) / 256), 256, 0, s>>>(
-                P.shells, P.npair, qbx_nc(P.lb), ncomp, d_shell_bf_, nbf_, dDJ, d_dpair_[pc], d_jpair_[pc]);
-            stats[0] += 1;
-        }
+    const int64_t NI2 = nint_ * nint_;
+    const unsigned pg = (unsigned)((NI2 + 255) / 256);
+    double *DJi = d_Dint_, *DKi = d_Dint_ + NI2;
+    k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDJ, DJi);
+    for (int m = 0; m < nmat; ++m)
+        k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDK + m * nbf_ * nbf_, DKi + m * NI2);
+    QBX_CUDA(cudaMemsetAsync(d_Jt_, 0, NI2 * sizeof(double), s));
+    QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * NI2 * sizeof(double), s));
+    QBX_CUDA(cudaMemsetAsync(dG, 0, nmat * nbf_ * nbf_ * sizeof(double), s));
+    stats[0] += 1 + nmat;
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc) {
             const TaskList &tl = tasks_[bc][kc];
             if (tl.n == 0) continue;
             const ClassOps *ops = qbx_class_ops(bc, kc);
-            if (mode_ == 0) {
-                Digest2Args d;
-                d.bra_shells = pairs_[bc].shells; d.ket_shells = pairs_[kc].shells;
-                d.tasks = tl.tasks; d.ntasks = tl.n; d.vals = vals_[bc][kc];
-                d.shell_bf = d_shell_bf_; d.nbf = (int)nbf_; d.nmat = nmat; d.same_class = (bc == kc);
-                d.DK = dDK; d.Kt = d_Kt_;
-                d.dbra = d_dpair_[bc]; d.dket = d_dpair_[kc]; d.jbra = d_jpair_[bc]; d.jket = d_jpair_[kc];
-                d.nbra = pairs_[bc].npair; d.nket = pairs_[kc].npair;
-                d.segs = tl.segs; d.nsegs = tl.nsegs;
-                const int rc2 = ops->digest2(d, s);
-                if (rc2 > 0) return rc2;
-                if (rc2 == 0) {
-                    stats[0] += 1;
-                    stats[5] += (double)tl.n * ops->ncomp * sizeof(double) * nmat;
-                    continue;
-                }
-            }
             DigestArgs a;
             a.bra_shells = pairs_[bc].shells; a.ket_shells = pairs_[kc].shells;
-            a.shell_bf = d_shell_bf_; a.nbf = (int)nbf_; a.nmat = nmat; a.same_class = (bc == kc);
-            a.DJ = dDJ; a.DK = dDK; a.Jt = d_Jt_; a.Kt = d_Kt_;
+            a.shell_first = d_shell_first_; a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
+            a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
                 int rc = ops->digest(a, s);
@@ -717,16 +673,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             }
         }
     if (mode_ == 1) stats[4] += model_flops_;
-    if (mode_ == 0)
-        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-            const DevPairSet &P = pairs_[pc];
-            const int ncomp = qbx_nc(P.la) * qbx_nc(P.lb);
-            if (P.npair == 0) continue;
-            k_pair_scatter<<<(unsigned)(((int64_t)P.npair * ncomp + 255) / 256), 256, 0, s>>>(
-                P.shells, P.npair, qbx_nc(P.lb), ncomp, d_shell_bf_, nbf_, d_jpair_[pc], d_Jt_);
-            stats[0] += 1;
-        }
-    k_finish_G<<<(unsigned)((N2 + 255) / 256), 256, 0, s>>>(nbf_, nmat, d_Jt_, d_Kt_, dG);
+    k_finish_G<<<pg, 256, 0, s>>>(nint_, nbf_, d_ext_of_int_, nmat, d_Jt_, d_Kt_, dG);
     QBX_CUDA(cudaGetLastError());
     stats[0] += 1;
     return QBX_OK;

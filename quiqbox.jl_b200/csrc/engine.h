@@ -23,25 +23,10 @@ struct DigestArgs {
     const int2 *tasks;
     int64_t ntasks;
     const double *vals;          // [ncomp][ntasks]
-    const int *shell_bf;         // [nshell][6]
-    int nbf, nmat, same_class;
-    const double *DJ, *DK;       // nbf^2, nmat * nbf^2
+    const int *shell_first;      // [nshell] first INTERNAL function index of each shell
+    int nbf, nmat, same_class;   // nbf = internal dimension here
+    const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
-};
-struct Digest2Args {
-    const int2 *bra_shells, *ket_shells;
-    const int2 *tasks;
-    int64_t ntasks;
-    const double *vals;
-    const int *shell_bf;
-    int nbf, nmat, same_class;
-    const double *DK;
-    double *Kt;
-    const double *dbra, *dket;   // DJ as pair vectors [comp][pair] of the bra / ket pair class
-    double *jbra, *jket;         // J accumulators, same layout
-    int nbra, nket;
-    const int2 *segs;            // (first task, count): runs of tasks sharing the bra pair
-    int nsegs;
 };
 struct ScatterArgs {
     const int2 *bra_shells, *ket_shells;
@@ -57,7 +42,6 @@ struct ClassOps {
     int la, lb, lc, ld, ncomp;
     int (*eri)(const ClassArgs &, cudaStream_t);
     int (*digest)(const DigestArgs &, cudaStream_t);
-    int (*digest2)(const Digest2Args &, cudaStream_t);     // returns -1 if the rows do not fit in shared memory
     int (*scatter)(const ScatterArgs &, cudaStream_t);
 };
 const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
@@ -74,8 +58,6 @@ struct DevPairSet {
 
 struct TaskList {
     int2 *tasks = nullptr;
-    int2 *segs = nullptr;                // bra-uniform runs (first task, count), <= QBX_SEG_MAX tasks each
-    int nsegs = 0;
     int64_t n = 0;
     double nprimq = 0;                   // primitive quartets behind these tasks
 };
@@ -119,7 +101,9 @@ private:
     double *chunk_ = nullptr;            // direct mode / tensor fill staging
     int64_t chunk_doubles_ = 0;
     double *d_Jt_ = nullptr, *d_Kt_ = nullptr;
-    double *d_dpair_[QBX_NPAIRCLS] = {nullptr}, *d_jpair_[QBX_NPAIRCLS] = {nullptr};
+    int *d_shell_first_ = nullptr, *d_ext_of_int_ = nullptr;
+    int64_t nint_ = 0;                   // internal dimension (complete Cartesian shells)
+    double *d_Dint_ = nullptr;           // DJ, DK[0], DK[1] in internal numbering
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -11,6 +11,7 @@
 #define QBX_MAX_L 2                 // class kernels cover s, p, d
 #define QBX_NPAIRCLS 6              // (ss) (ps) (pp) (ds) (dp) (dd)
 #define QBX_NCLASS 21               // canonical quartet classes, bra pair class >= ket pair class
+#define QBX_COOP_ACC 180             // >= this many [e0|f0] accumulators: warp-cooperative ERI kernel
 #define QBX_GEN_MAXL 64             // generic kernel: max total angular momentum of a quartet
 #define QBX_GEN_MAXAX 32            // generic kernel: max angular momentum sum on one axis
 
