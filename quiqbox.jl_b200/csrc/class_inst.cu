@@ -35,7 +35,9 @@ static int launch_eri(const ClassArgs &a, cudaStream_t s)
 static int launch_digest(const DigestArgs &a, cudaStream_t s)
 {
     if (a.ntasks <= 0) return QBX_OK;
-    digest_kernel<QLA, QLB, QLC, QLD><<<(unsigned)((a.ntasks + 127) / 128), 128, 0, s>>>(a);
+    const int64_t nblk = (a.ntasks + 127) / 128;
+    const int64_t R = nblk < a.spread ? nblk : a.spread, C = (nblk + R - 1) / R;
+    digest_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(R * C), 128, 0, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }

@@ -26,6 +26,8 @@
 #pragma once
 #include "engine.h"
 
+#define QBX_DIGEST_SPREAD 384
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -33,67 +35,52 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Latency notes (ncu, profiles/r01): the kernel is bound by exposed memory latency, not by
+// any throughput, so the body is organised as few dependent steps as possible:
+//   task -> one int4 record per pair (shells + first function indices) -> all densities and
+//   the values of one (a,b) slice as independent loads -> FMAs -> all shuffles/REDs at the end.
+// Values are read once and feed J and K together (the second exchange density of a UHF build
+// re-reads them).
 template <int LA, int LB, int LC, int LD>
 __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
 {
-    constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD);
-    const int64_t q0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NCD = NCc * ND;
+    // Block order is transposed against task order: the blocks resident at one time sit
+    // spread-th of the list apart, i.e. on different bra rows.  In task order they would
+    // all update the same few hundred G elements, and fp64 REDs on a hot set that small run at
+    // 1e10/s instead of 2e11/s on B200 (tools/redbench.cu; profiles/r01/redbench.md).
+    const int64_t nblk = (p.ntasks + 127) / 128;
+    const int64_t R = nblk < p.spread ? nblk : p.spread, C = (nblk + R - 1) / R;
+    const int64_t blk = (blockIdx.x % R) * C + blockIdx.x / R;
+    if (blk >= nblk) return;
+    const int64_t q0 = blk * 128 + threadIdx.x;
     if (q0 - (threadIdx.x & 31) >= p.ntasks) return;          // whole warp past the end
     const bool valid = q0 < p.ntasks;
     const int64_t q = valid ? q0 : p.ntasks - 1;
     const int2 t = p.tasks[q];
-    const int2 sb = p.bra_shells[t.x], sk = p.ket_shells[t.y];
+    const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);   // (shell A, shell B, first A, first B)
     double f = valid ? 1.0 : 0.0;
-    if (sb.x == sb.y) f *= 0.5;
-    if (sk.x == sk.y) f *= 0.5;
+    if (rb.x == rb.y) f *= 0.5;
+    if (rk.x == rk.y) f *= 0.5;
     if (p.same_class && t.x == t.y) f *= 0.5;
     const bool uniAB = __all_sync(0xffffffffu, t.x == __shfl_sync(0xffffffffu, t.x, 0));
-    const bool uniC = uniAB && __all_sync(0xffffffffu, sk.x == __shfl_sync(0xffffffffu, sk.x, 0));
+    const bool uniC = uniAB && __all_sync(0xffffffffu, rk.x == __shfl_sync(0xffffffffu, rk.x, 0));
     const bool lane0 = (threadIdx.x & 31) == 0;
     const int64_t N = p.nbf;                                  // internal dimension
-    const int ia = p.shell_first[sb.x], ib = p.shell_first[sb.y];
-    const int ic = p.shell_first[sk.x], id = p.shell_first[sk.y];
+    const int ia = rb.z, ib = rb.w, ic = rk.z, id = rk.w;
     const double *vq = p.vals + q;
 
-    // ---- Coulomb
-    double dcd[NCc * ND], jcd[NCc * ND];
-#pragma unroll
-    for (int c = 0; c < NCc; ++c)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) { dcd[c * ND + d] = p.DJ[(id + d) + N * (ic + c)]; jcd[c * ND + d] = 0.0; }
-#pragma unroll
-    for (int a = 0; a < NA; ++a)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const double dab = p.DJ[(ib + b) + N * (ia + a)];
-            double jab = 0.0;
-#pragma unroll
-            for (int cd = 0; cd < NCc * ND; ++cd) {
-                const double v = vq[(int64_t)((a * NB + b) * NCc * ND + cd) * p.ntasks];
-                jab = fma(dcd[cd], v, jab);
-                jcd[cd] = fma(dab, v, jcd[cd]);
-            }
-            jab *= 2.0 * f;
-            if (uniAB) {
-                jab = warp_sum(jab);
-                if (lane0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), jab);
-            } else if (valid) {
-                atomicAdd(p.Jt + (ib + b) + N * (ia + a), jab);
-            }
-        }
-    if (valid) {
-#pragma unroll
-        for (int c = 0; c < NCc; ++c)
-#pragma unroll
-            for (int d = 0; d < ND; ++d) atomicAdd(p.Jt + (id + d) + N * (ic + c), 2.0 * f * jcd[c * ND + d]);
-    }
-
-    // ---- exchange, one density at a time
     for (int m = 0; m < p.nmat; ++m) {
         const double *DK = p.DK + m * N * N;
         double *Kt = p.Kt + m * N * N;
+        const bool coul = (m == 0);
+        double dcd[NCD], jcd[NCD], jab[NA * NB];
         double dac[NA * NCc], dad[NA * ND], dbc[NB * NCc], dbd[NB * ND];
         double kac[NA * NCc], kad[NA * ND], kbc[NB * NCc], kbd[NB * ND];
+#pragma unroll
+        for (int c = 0; c < NCc; ++c)
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { dcd[c * ND + d] = coul ? p.DJ[(id + d) + N * (ic + c)] : 0.0; jcd[c * ND + d] = 0.0; }
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
 #pragma unroll
@@ -111,31 +98,61 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
+            for (int b = 0; b < NB; ++b) {
+                const double dab = coul ? p.DJ[(ib + b) + N * (ia + a)] : 0.0;
+                double v[NCD];
+#pragma unroll
+                for (int cd = 0; cd < NCD; ++cd) v[cd] = f * vq[(int64_t)((a * NB + b) * NCD + cd) * p.ntasks];
+                double j = 0.0;
 #pragma unroll
                 for (int c = 0; c < NCc; ++c)
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
-                        const double v = f * vq[(int64_t)(((a * NB + b) * NCc + c) * ND + d) * p.ntasks];
-                        kac[a * NCc + c] = fma(dbd[b * ND + d], v, kac[a * NCc + c]);
-                        kad[a * ND + d] = fma(dbc[b * NCc + c], v, kad[a * ND + d]);
-                        kbc[b * NCc + c] = fma(dad[a * ND + d], v, kbc[b * NCc + c]);
-                        kbd[b * ND + d] = fma(dac[a * NCc + c], v, kbd[b * ND + d]);
+                        const double x = v[c * ND + d];
+                        j = fma(dcd[c * ND + d], x, j);
+                        jcd[c * ND + d] = fma(dab, x, jcd[c * ND + d]);
+                        kac[a * NCc + c] = fma(dbd[b * ND + d], x, kac[a * NCc + c]);
+                        kad[a * ND + d] = fma(dbc[b * NCc + c], x, kad[a * ND + d]);
+                        kbc[b * NCc + c] = fma(dad[a * ND + d], x, kbc[b * NCc + c]);
+                        kbd[b * ND + d] = fma(dac[a * NCc + c], x, kbd[b * ND + d]);
                     }
+                jab[a * NB + b] = j;
+            }
+        // ---- updates (f is already folded into the values)
+        if (coul) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    double j = 2.0 * jab[a * NB + b];
+                    if (uniAB) {
+                        j = warp_sum(j);
+                        if (lane0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
+                    } else if (valid) {
+                        atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
+                    }
+                }
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < NCc; ++c)
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) atomicAdd(p.Jt + (id + d) + N * (ic + c), 2.0 * jcd[c * ND + d]);
+            }
+        }
         if (uniC) {                                           // K[ac], K[bc]: one address per warp
 #pragma unroll
             for (int a = 0; a < NA; ++a)
 #pragma unroll
                 for (int c = 0; c < NCc; ++c) {
-                    const double v = warp_sum(kac[a * NCc + c]);
-                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ia + a), v);
+                    const double x = warp_sum(kac[a * NCc + c]);
+                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ia + a), x);
                 }
 #pragma unroll
             for (int b = 0; b < NB; ++b)
 #pragma unroll
                 for (int c = 0; c < NCc; ++c) {
-                    const double v = warp_sum(kbc[b * NCc + c]);
-                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ib + b), v);
+                    const double x = warp_sum(kbc[b * NCc + c]);
+                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ib + b), x);
                 }
         } else if (valid) {
 #pragma unroll

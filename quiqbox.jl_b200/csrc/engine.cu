@@ -1,5 +1,6 @@
 // Host orchestration of the shell-quartet path (see engine.h).
 #include "engine.h"
+#include "digest.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -384,9 +385,22 @@ int Engine::upload(bool pair_adjacent)
         for (size_t a = 0; a < ns; ++a)           // shells are sorted by l, so a >= b implies la >= lb
             for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
     }
+    std::vector<int> first_h(ns);
+    { int acc = 0; for (size_t s = 0; s < ns; ++s) { first_h[s] = acc; acc += qbx_nc(shells_[s].l); } }
     for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], false, pairs_[pc]);   // keep (A major, B ascending)
+        // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
+        // equal-count group a run of pairs shares A and walks over consecutive B
+        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc]);
         if (rc) return rc;
+        {
+            DevPairSet &P = pairs_[pc];
+            std::vector<int2> sh(P.npair);
+            if (P.npair) QBX_CUDA(cudaMemcpy(sh.data(), P.shells, P.npair * sizeof(int2), cudaMemcpyDeviceToHost));
+            std::vector<int4> info(P.npair);
+            for (int i = 0; i < P.npair; ++i) info[i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
+            QBX_CUDA(cudaMalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
+            if (P.npair) QBX_CUDA(cudaMemcpy(P.info, info.data(), info.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
     }
     QBX_CUDA(cudaEventCreate(&ev0_));
     QBX_CUDA(cudaEventCreate(&ev1_));
@@ -396,7 +410,7 @@ int Engine::upload(bool pair_adjacent)
 Engine::~Engine()
 {
     release_store();
-    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); }
+    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); cudaFree(p.info); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_); cudaFree(d_shell_first_); cudaFree(d_ext_of_int_); cudaFree(d_Dint_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
 
@@ -650,8 +664,10 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             if (tl.n == 0) continue;
             const ClassOps *ops = qbx_class_ops(bc, kc);
             DigestArgs a;
-            a.bra_shells = pairs_[bc].shells; a.ket_shells = pairs_[kc].shells;
-            a.shell_first = d_shell_first_; a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
+            a.bra_info = pairs_[bc].info; a.ket_info = pairs_[kc].info;
+            static const int spread = getenv("QBX_DIGEST_SPREAD") ? atoi(getenv("QBX_DIGEST_SPREAD")) : QBX_DIGEST_SPREAD;
+            a.spread = spread > 0 ? spread : 1;
+            a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];

@@ -19,12 +19,12 @@ struct HostShell {
 
 // arguments of the per-class consumers of a packed value block
 struct DigestArgs {
-    const int2 *bra_shells, *ket_shells;
+    const int4 *bra_info, *ket_info;  // per pair: (shell A, shell B, first internal function of A, of B)
     const int2 *tasks;
     int64_t ntasks;
     const double *vals;          // [ncomp][ntasks]
-    const int *shell_first;      // [nshell] first INTERNAL function index of each shell
     int nbf, nmat, same_class;   // nbf = internal dimension here
+    int spread;                  // number of block slots the task list is dealt over (see digest.cuh)
     const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
 };
@@ -52,6 +52,7 @@ struct DevPairSet {
     int *prim_off = nullptr;
     double *geom = nullptr, *prim = nullptr, *schwarz = nullptr, *soa = nullptr;
     int2 *soa_idx = nullptr;
+    int4 *info = nullptr;                // (shell A, shell B, first internal function of A, of B)
     std::vector<int> h_nprim;            // primitive pairs per pair (host copy, for cost models)
     PairSet view() const { return PairSet{shells, prim_off, geom, prim, soa, soa_idx, npair}; }
 };
