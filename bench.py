@@ -270,14 +270,17 @@ def main():
         DJh, DKh, Gh = np.asfortranarray(2 * Dh), np.asfortranarray(Dh), np.zeros(n * n)
         h2d = sum(a.nbytes for a in arrs) + DJh.nbytes + DKh.nbytes
         times = []
-        for it in range(1 + max(1, min(args.steps, 2))):
+        for it in range(1 + max(2, min(args.steps, 3))):
             barrier()
             t0 = time.perf_counter()
             h = C.c_void_p()
             L.check(lib.qbx_basis_create(mod.nprim, L.ptr(arrs[0]), L.ptr(arrs[1]), L.ptr(arrs[2]), mod.nbf, L.ptr(arrs[3]),
                                          L.ptr(arrs[4]), L.ptr(arrs[5]), C.byref(h)))
+            t1 = time.perf_counter()
             L.check(lib.qbx_eri_store(h, args.screen, 0, rank, world))
+            t2 = time.perf_counter()
             L.check(lib.qbx_fock_build(h, 1, L.ptr(DJh), L.ptr(DKh), L.ptr(Gh)))
+            phases = [t1 - t0, t2 - t1, time.perf_counter() - t2]
             if world > 1:
                 g = torch.from_numpy(Gh).cuda(); dist.all_reduce(g); Gh[:] = g.cpu().numpy()
             torch.cuda.synchronize()
@@ -285,11 +288,12 @@ def main():
             lib.qbx_basis_destroy(h)
             if it > 0:
                 times.append(dt)
-        t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+        t = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": tot_values / t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(Gh.nbytes), "seconds_per_step": t.item(),
+               "phase_seconds_rank0": {"qbx_basis_create": phases[0], "qbx_eri_store": phases[1], "qbx_fock_build": phases[2]},
                "path": "qbx_basis_create -> qbx_eri_store(stored) -> qbx_fock_build (host D, host G) -> qbx_basis_destroy"}
 
     if rank == 0:

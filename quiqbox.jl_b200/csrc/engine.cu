@@ -116,7 +116,10 @@ __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk
     cnt[i] = c;
 }
 
-#define QBX_TASK_CHUNK 4096
+// Sharding granule: rank r owns chunks r, r + nranks, ...  One chunk = one ERI block (256 tasks).
+// It must be much shorter than a bra row (up to ~6000 kets whose cost falls 81-fold along the
+// row): with 4096-task chunks the round-robin aliased with the rows and rank 0 was 2x slower.
+#define QBX_TASK_CHUNK 256
 // one warp per bra row: compact the surviving kets in order; keep the chunks of this rank
 __global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol,
                              const int64_t *rowoff, int rank, int nranks, int2 *tasks)

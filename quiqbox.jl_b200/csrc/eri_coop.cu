@@ -259,6 +259,20 @@ __device__ __forceinline__ void boys_rt(const BoysTable &tb, double T, double sc
 }
 
 #define COOP_WARPS 4
+#define COOP_BATCH 4
+
+// op record i of a level, or a harmless self-referencing dummy past the end
+__device__ __forceinline__ Op ld_op(const Op *ops, int i, int n)
+{
+    Op o;
+    if (i < n) {
+        const int4 r = __ldg(reinterpret_cast<const int4 *>(ops + i));
+        o = *reinterpret_cast<const Op *>(&r);
+    } else {
+        o.dst = 0; o.a = 0; o.b = 0; o.c = -1; o.d = -1; o.ax = 0; o.n1 = 0; o.n2 = 0;
+    }
+    return o;
+}
 
 __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
 {
@@ -295,32 +309,59 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
                 __syncwarp();                              // previous accumulate has read S
                 if (lane <= p.L) B[lane] = Fm[lane];
                 __syncwarp();
+                // Entries of one level are independent, so each lane takes COOP_BATCH of them at a
+                // time: all op records first (global, L1/L2), then all sources (shared), then the
+                // arithmetic and the stores -- otherwise every entry pays the full load latency.
                 for (int lv = 0; lv < p.nvrr; ++lv) {
                     const Op *ops = p.ops + p.vrr[lv].first;
-                    for (int i = lane; i < p.vrr[lv].count; i += 32) {
-                        const Op o = ops[i];
-                        double v = fma(PA[o.ax], B[o.a], WP[o.ax] * B[o.b]);
-                        if (o.c >= 0) v = fma(o.n1 * i2z, fma(-rz, B[o.d], B[o.c]), v);
-                        B[o.dst] = v;
+                    const int n = p.vrr[lv].count;
+                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
+                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH], sc[COOP_BATCH], sd[COOP_BATCH];
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) {
+                            sa[u] = B[o[u].a]; sb[u] = B[o[u].b];
+                            sc[u] = o[u].c >= 0 ? B[o[u].c] : 0.0; sd[u] = o[u].c >= 0 ? B[o[u].d] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u)
+                            if (i0 + 32 * u < n)
+                                B[o[u].dst] = fma(o[u].n1 * i2z, fma(-rz, sd[u], sc[u]), fma(PA[o[u].ax], sa[u], WP[o[u].ax] * sb[u]));
                     }
                     __syncwarp();
                 }
                 for (int lv = 0; lv < p.nxfer; ++lv) {
                     const Op *ops = p.ops + p.xfer[lv].first;
-                    for (int i = lane; i < p.xfer[lv].count; i += 32) {
-                        const Op o = ops[i];
-                        double v = fma(k0[o.ax], B[o.a], -zoe * B[o.b]);
-                        if (o.c >= 0) v = fma(o.n1 * i2e, B[o.c], v);
-                        if (o.d >= 0) v = fma(o.n2 * i2e, B[o.d], v);
-                        B[o.dst] = v;
+                    const int n = p.xfer[lv].count;
+                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
+                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH], sc[COOP_BATCH], sd[COOP_BATCH];
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) {
+                            sa[u] = B[o[u].a]; sb[u] = B[o[u].b];
+                            sc[u] = o[u].c >= 0 ? B[o[u].c] : 0.0; sd[u] = o[u].d >= 0 ? B[o[u].d] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u)
+                            if (i0 + 32 * u < n)
+                                B[o[u].dst] = fma(o[u].n2 * i2e, sd[u], fma(o[u].n1 * i2e, sc[u], fma(k0[o[u].ax], sa[u], -zoe * sb[u])));
                     }
                     __syncwarp();
                 }
                 {
                     const Op *ops = p.ops + p.acc.first;
-                    for (int i = lane; i < p.acc.count; i += 32) {
-                        const Op o = ops[i];
-                        B[o.dst] += B[o.a];
+                    const int n = p.acc.count;
+                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
+                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH];
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u) { sa[u] = B[o[u].a]; sb[u] = B[o[u].dst]; }
+#pragma unroll
+                        for (int u = 0; u < COOP_BATCH; ++u)
+                            if (i0 + 32 * u < n) B[o[u].dst] = sb[u] + sa[u];
                     }
                 }
             }
@@ -328,11 +369,19 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
         __syncwarp();
         for (int lv = 0; lv < p.nhrr; ++lv) {
             const Op *ops = p.ops + p.hrr[lv].first;
-            for (int i = lane; i < p.hrr[lv].count; i += 32) {
-                const Op o = ops[i];
-                double v = B[o.a];
-                if (o.ax >= 0) v = fma(o.n2 ? CD[o.ax] : AB[o.ax], B[o.b], v);
-                B[o.dst] = v;
+            const int n = p.hrr[lv].count;
+            for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
+                Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH];
+#pragma unroll
+                for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
+#pragma unroll
+                for (int u = 0; u < COOP_BATCH; ++u) { sa[u] = B[o[u].a]; sb[u] = o[u].ax >= 0 ? B[o[u].b] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < COOP_BATCH; ++u)
+                    if (i0 + 32 * u < n) {
+                        const int ax = o[u].ax >= 0 ? o[u].ax : 0;
+                        B[o[u].dst] = fma(o[u].n2 ? CD[ax] : AB[ax], sb[u], sa[u]);
+                    }
             }
             __syncwarp();
         }
