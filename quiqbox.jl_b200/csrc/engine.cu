@@ -415,7 +415,7 @@ Engine::~Engine()
     release_store();
     for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); cudaFree(p.info); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_); cudaFree(d_shell_first_); cudaFree(d_ext_of_int_); cudaFree(d_Dint_);
-    cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_);
+    cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_); cudaFree(d_counters_);
 
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -459,6 +459,10 @@ int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, c
     a.tasks = tasks; a.ntasks = n; a.out = out;
     a.shell_scale = d_shell_scale_;
     a.boys = qbx_boys_table();
+    if (!d_counters_) QBX_CUDA(cudaMalloc(&d_counters_, 1024 * sizeof(unsigned int)));
+    a.counter = d_counters_ + counter_next_;
+    counter_next_ = (counter_next_ + 1) % 1024;
+    QBX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), s));
     // Large classes (>= coop_min contracted accumulators per quartet) go to the warp-cooperative
     // kernel; QBX_COOP_MIN_ACC overrides the threshold (0 = every class, for tests).
     static const int coop_min = std::min(QBX_COOP_ACC, getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : QBX_COOP_ACC);

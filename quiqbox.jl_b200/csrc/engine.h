@@ -107,6 +107,8 @@ private:
     double *d_Dint_ = nullptr;           // DJ, DK[0], DK[1] in internal numbering
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;
+    unsigned int *d_counters_ = nullptr; // work-queue heads, one per ERI launch (rotating)
+    int counter_next_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     cudaEvent_t cls_ev_[QBX_NCLASS + 1] = {nullptr};
     bool cls_timed_ = false;

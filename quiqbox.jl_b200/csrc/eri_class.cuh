@@ -79,6 +79,7 @@ struct ClassArgs {
     double *out;               // [ncomp][ntasks]
     const double *shell_scale; // [nshell][6] per-component weights
     BoysTable boys;
+    unsigned int *counter;     // work queue head for this launch (zeroed by the host)
 };
 
 __device__ __forceinline__ double4 ldg4(const double *p)
@@ -292,16 +293,27 @@ struct EriClass {
 #define QBX_ERI_THREADS 256
 
 // Persistent blocks: the Boys columns of this class are staged in shared memory once, then
-// the block walks the task list with a grid stride (tasks are sorted by cost, so the stride
-// interleaves heavy and light chunks over the SMs).
+// the block pulls chunks of 256 consecutive tasks from a global work queue.  The list is
+// ordered heavy-first (rows by bra contraction length, kets likewise), and a single task spans
+// 1 to 6561 primitive quartets, so a static grid-stride assignment leaves most of the GPU idle
+// behind the few threads that drew a heavy task (it halved the throughput at 1/8 of the list,
+// i.e. on 8 GPUs); with the queue the light chunks at the end fill the tail.
 template <int LA, int LB, int LC, int LD>
 __global__ void __launch_bounds__(QBX_ERI_THREADS) eri_class_kernel(ClassArgs p)
 {
     using EC = EriClass<LA, LB, LC, LD>;
     extern __shared__ double boys_smem[];
+    __shared__ unsigned int s_chunk;
     boys_stage_smem<EC::L>(p.boys, boys_smem);
-    __syncthreads();
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < p.ntasks; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t nchunk = (p.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int64_t chunk = s_chunk;
+        if (chunk >= nchunk) break;
+        const int64_t q = chunk * QBX_ERI_THREADS + threadIdx.x;
+        if (q >= p.ntasks) continue;
         const int2 t = p.tasks[q];
         const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
         const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
