@@ -123,7 +123,9 @@ int qbx_eri_recompute_async(qbx_basis *b);
  * collectives and CUDA events with the library's kernels on one stream. */
 int qbx_set_stream(void *stream);
 
-/* Per-class device times of the most recent qbx_eri_recompute[_async] (synchronises).
+/* Per-class device times: runs one extra recompute with the class kernels serialised on the
+ * library's stream and CUDA events around each of them (the normal recompute overlaps the
+ * classes on side streams), then synchronises.
  * out[21][6]: la*1000+lb*100+lc*10+ld, seconds, shell quartets, primitive quartets,
  * model flops, component values.  Rows follow the canonical class order. */
 int qbx_class_stats(qbx_basis *b, double *out);

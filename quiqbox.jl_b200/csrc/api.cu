@@ -297,7 +297,7 @@ extern "C" int qbx_class_stats(qbx_basis *b, double *out)
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     if (!b->eng) { qbx_set_error("qbx_class_stats: basis has no shell-class path"); return QBX_ERR_STATE; }
-    return b->eng->class_stats(out);
+    return b->eng->class_stats(g_stream, b->stats, out);
 }
 
 // register-resident DFMA chains: 8 independent accumulators per thread

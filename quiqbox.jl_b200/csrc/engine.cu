@@ -418,6 +418,8 @@ Engine::~Engine()
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_); cudaFree(d_counters_);
 
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < kSide; ++i) { if (side_[i]) cudaStreamDestroy(side_[i]); if (side_ev_[i]) cudaEventDestroy(side_ev_[i]); }
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
 }
@@ -607,31 +609,60 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
     return QBX_OK;
 }
 
-int Engine::recompute(cudaStream_t s, double *stats)
+int Engine::fork(cudaStream_t s)
+{
+    if (!fork_ev_) {
+        QBX_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+        for (int i = 0; i < kSide; ++i) {
+            QBX_CUDA(cudaStreamCreateWithFlags(&side_[i], cudaStreamNonBlocking));
+            QBX_CUDA(cudaEventCreateWithFlags(&side_ev_[i], cudaEventDisableTiming));
+        }
+    }
+    QBX_CUDA(cudaEventRecord(fork_ev_, s));
+    for (int i = 0; i < kSide; ++i) QBX_CUDA(cudaStreamWaitEvent(side_[i], fork_ev_, 0));
+    return QBX_OK;
+}
+
+int Engine::join(cudaStream_t s)
+{
+    for (int i = 0; i < kSide; ++i) {
+        QBX_CUDA(cudaEventRecord(side_ev_[i], side_[i]));
+        QBX_CUDA(cudaStreamWaitEvent(s, side_ev_[i], 0));
+    }
+    return QBX_OK;
+}
+
+int Engine::recompute(cudaStream_t s, double *stats, bool timed)
 {
     if (mode_ != 0) { qbx_set_error("recompute: stored mode only"); return QBX_ERR_STATE; }
-    int c = 0;
+    int rc;
+    if (!timed && (rc = fork(s))) return rc;
+    int c = 0, k = 0;
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc, ++c) {
-            if (!cls_ev_[c]) QBX_CUDA(cudaEventCreate(&cls_ev_[c]));
-            QBX_CUDA(cudaEventRecord(cls_ev_[c], s));
+            if (timed) {
+                if (!cls_ev_[c]) QBX_CUDA(cudaEventCreate(&cls_ev_[c]));
+                QBX_CUDA(cudaEventRecord(cls_ev_[c], s));
+            }
             const TaskList &tl = tasks_[bc][kc];
             if (tl.n == 0) continue;
-            int rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], s);
-            if (rc) return rc;
+            if ((rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], timed ? s : side_[k++ % kSide]))) return rc;
             stats[0] += 1;
         }
-    if (!cls_ev_[QBX_NCLASS]) QBX_CUDA(cudaEventCreate(&cls_ev_[QBX_NCLASS]));
-    QBX_CUDA(cudaEventRecord(cls_ev_[QBX_NCLASS], s));
-    cls_timed_ = true;
+    if (timed) {
+        if (!cls_ev_[QBX_NCLASS]) QBX_CUDA(cudaEventCreate(&cls_ev_[QBX_NCLASS]));
+        QBX_CUDA(cudaEventRecord(cls_ev_[QBX_NCLASS], s));
+        cls_timed_ = true;
+    } else if ((rc = join(s))) return rc;
     stats[3] += n_primq_;
     stats[4] += model_flops_;
     return QBX_OK;
 }
 
-int Engine::class_stats(double *out)
+int Engine::class_stats(cudaStream_t s, double *stats, double *out)
 {
-    if (!cls_timed_) { qbx_set_error("qbx_class_stats: no recompute has run"); return QBX_ERR_STATE; }
+    int rc = recompute(s, stats, true);
+    if (rc) return rc;
     QBX_CUDA(cudaEventSynchronize(cls_ev_[QBX_NCLASS]));
     int c = 0;
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
@@ -665,6 +696,8 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
     QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * NI2 * sizeof(double), s));
     QBX_CUDA(cudaMemsetAsync(dG, 0, nmat * nbf_ * nbf_ * sizeof(double), s));
     stats[0] += 1 + nmat;
+    int kside = 0;
+    if (mode_ == 0) { int rc = fork(s); if (rc) return rc; }
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc) {
             const TaskList &tl = tasks_[bc][kc];
@@ -678,7 +711,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
-                int rc = ops->digest(a, s);
+                int rc = ops->digest(a, side_[kside++ % kSide]);
                 if (rc) return rc;
                 stats[0] += 1;
                 stats[5] += (double)tl.n * ops->ncomp * sizeof(double);
@@ -696,6 +729,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             }
         }
     if (mode_ == 1) stats[4] += model_flops_;
+    if (mode_ == 0) { int rc = join(s); if (rc) return rc; }
     k_finish_G<<<pg, 256, 0, s>>>(nint_, nbf_, d_ext_of_int_, nmat, d_Jt_, d_Kt_, dG);
     QBX_CUDA(cudaGetLastError());
     stats[0] += 1;

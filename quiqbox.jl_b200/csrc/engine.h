@@ -73,8 +73,8 @@ public:
     void info(int64_t *info) const;
     int fill_tensor(double *d_tensor, cudaStream_t s, double *stats);
     int store(double tol, int mode, int rank, int nranks, cudaStream_t s, double *stats);
-    int recompute(cudaStream_t s, double *stats);          // enqueue only; per-class events recorded
-    int class_stats(double *out);                          // synchronises on the last recompute
+    int recompute(cudaStream_t s, double *stats, bool timed = false);   // enqueue only; timed = serialised, per-class events
+    int class_stats(cudaStream_t s, double *stats, double *out);        // runs one serialised, timed recompute
     int fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats);
     void release_store();
 
@@ -107,6 +107,13 @@ private:
     double *d_Dint_ = nullptr;           // DJ, DK[0], DK[1] in internal numbering
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;
+    // the 21 class kernels of a pass are independent: they are dealt over a few side streams so
+    // that the tail of one class overlaps the head of the next
+    static constexpr int kSide = 4;
+    cudaStream_t side_[kSide] = {nullptr};
+    cudaEvent_t side_ev_[kSide] = {nullptr}, fork_ev_ = nullptr;
+    int fork(cudaStream_t s);
+    int join(cudaStream_t s);
     unsigned int *d_counters_ = nullptr; // work-queue heads, one per ERI launch (rotating)
     int counter_next_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
