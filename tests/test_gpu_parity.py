@@ -287,3 +287,44 @@ assert err < 1e-12
     env = dict(os.environ, QBX_COOP_MIN_ACC="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ BASELINE.json configs [2] and [3]
+def test_benzene_and_water_dimer_scf_vs_oracle_energy():
+    g = json.load(open(os.path.join(HERE, "golden", "oracle_energies.json")))
+    for key, mol in (("(H2O)2/cc-pVDZ/RHF", water_cluster(2)), ("benzene/cc-pVDZ/RHF", benzene())):
+        nuc, xyz = mol
+        r = qb.runHartreeFock((nuc, xyz), mol_basis(nuc, xyz, "cc-pVDZ"), qb.HFconfig(initial=":CoreH"), screen_tol=1e-13)
+        assert r.converged, key
+        assert sum(r.energy) == pytest.approx(g[key], abs=1e-8), key     # north-star bar: 1e-8 Ha
+
+
+def test_water16_full_size_properties():
+    """(H2O)16/cc-pVDZ, the metric's configuration (400 functions, 1.7e8 shell quartets).  The oracle
+    cannot produce its energy in reasonable time (~28 h), so the full size is covered by
+    size-independent properties: sampled ERIs vs the oracle, stored == direct, screened ~ unscreened,
+    Hermitian G, linearity, and an SCF that converges to the same energy in both modes."""
+    nuc, xyz = water_cluster(16)
+    bs = mol_basis(nuc, xyz, "cc-pVDZ")
+    db, idx, ref = _sampled_eri_check(bs, 150, 99)
+    assert db.nbf == 400
+    assert np.max(np.abs(qb.elecRepulsionList(db, idx) - ref)) < ERI_ATOL
+    n = db.nbf
+    DJ, DK = _rand_sym(n, 41) / n, _rand_sym(n, 42) / n
+    st = qb.DeviceERI(db, mode="stored", screen_tol=1e-12)
+    Gs = st.getGcore(DJ, [DK])[0]
+    assert np.array_equal(Gs, Gs.T)
+    assert np.max(np.abs(st.getGcore(3 * DJ, [3 * DK])[0] - 3 * Gs)) < 1e-10
+    G0 = qb.DeviceERI(db, mode="stored", screen_tol=0.0).getGcore(DJ, [DK])[0]      # 25.7 GB packed store
+    assert db.info()["n_values"] == 3_250_000_000 + 1_340_000 or db.info()["n_values"] > 3.2e9
+    assert np.max(np.abs(Gs - G0)) < 1e-9
+    Gd = qb.DeviceERI(db, mode="direct", screen_tol=1e-12).getGcore(DJ, [DK])[0]
+    assert np.max(np.abs(Gs - Gd)) < 1e-10
+    cfg = qb.HFconfig(initial=":CoreH", strategy=qb.SCFconfig(threshold=1e-9))
+    e = {}
+    for mode in ("stored", "direct"):
+        r = qb.runHartreeFock((nuc, xyz), db, cfg, mode=mode)
+        assert r.converged, mode
+        e[mode] = sum(r.energy)
+    assert e["stored"] == pytest.approx(e["direct"], abs=1e-8)
+    assert -1217.5 < e["stored"] < -1216.0                     # 16 x E(H2O/cc-pVDZ) = -1216.43 plus binding
