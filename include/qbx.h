@@ -109,10 +109,13 @@ int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
 /* Synthetic throughput sweep: nquartets contracted shell quartets of class
  * (la lb|lc ld) with uniform contraction degree K, generated from `seed` (centres uniform in
  * a 10-bohr cube, exponents log-uniform in [0.1,1e3], coefficients in [-1,1]).  secs: device
- * time of the ERI kernel, checksum: sum of all values.  sample_out (may be NULL): the first
- * min(nsample, nquartets) quartets' values and sample_geom their inputs, for oracle checks. */
+ * time of the ERI kernel, checksum: sum of all values, prim_quartets (may be NULL): primitive
+ * shell quartets actually evaluated (primitive pairs whose prefactor underflows are dropped, so
+ * this is <= nquartets * K^4).  sample_out (may be NULL): the first min(nsample, nquartets)
+ * quartets' values and sample_geom their inputs, for oracle checks. */
 int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed,
-                   double *secs, double *checksum, int64_t nsample, double *sample_out, double *sample_geom);
+                   double *secs, double *checksum, double *prim_quartets, int64_t nsample,
+                   double *sample_out, double *sample_geom);
 
 /* Asynchronous variant of qbx_eri_recompute: only enqueues the class kernels on the
  * library's stream (see qbx_set_stream). */

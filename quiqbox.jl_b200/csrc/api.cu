@@ -435,7 +435,8 @@ extern "C" int qbx_boys(int64_t n, const double *T, int mmax, int table, double 
 }
 
 extern "C" int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed, double *secs,
-                              double *checksum, int64_t nsample, double *sample_out, double *sample_geom)
+                              double *checksum, double *prim_quartets, int64_t nsample, double *sample_out,
+                              double *sample_geom)
 {
     if (la < 0 || la > QBX_MAX_L || lb < 0 || lb > la || lc < 0 || lc > QBX_MAX_L || ld < 0 || ld > lc || K < 1 ||
         K > 16 || nquartets <= 0 || !secs || !checksum) {
@@ -444,7 +445,8 @@ extern "C" int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nqu
     }
     int rc = ensure_init();
     if (rc) return rc;
-    return Engine::synthetic(la, lb, lc, ld, K, nquartets, seed, secs, checksum, nsample, sample_out, sample_geom, g_stream);
+    return Engine::synthetic(la, lb, lc, ld, K, nquartets, seed, secs, checksum, prim_quartets, nsample, sample_out, sample_geom,
+                             g_stream);
 }
 
 extern "C" int qbx_stats(qbx_basis *b, double *out, int reset)

@@ -738,7 +738,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
 
 // ------------------------------------------------------------------ synthetic class batches
 int Engine::synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_t seed, double *secs, double *checksum,
-                      int64_t nsample, double *sample_out, double *sample_geom, cudaStream_t s)
+                      double *prim_quartets, int64_t nsample, double *sample_out, double *sample_geom, cudaStream_t s)
 {
     if (pair_cls(la, lb) < pair_cls(lc, ld)) { std::swap(la, lc); std::swap(lb, ld); }
     const int bc = pair_cls(la, lb), kc = pair_cls(lc, ld);
@@ -771,6 +771,11 @@ int Engine::synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_
     const int koff = (bc == kc) ? (int)np : 0;
     std::vector<int2> tasks((size_t)nq);
     for (int64_t q = 0; q < nq; ++q) tasks[q] = make_int2((int)(q / np), koff + (int)(q % np));
+    if (prim_quartets) {
+        double tot = 0;
+        for (int64_t q = 0; q < nq; ++q) tot += (double)e->pairs_[bc].h_nprim[tasks[q].x] * (double)e->pairs_[kc].h_nprim[tasks[q].y];
+        *prim_quartets = tot;
+    }
     int2 *d_t = nullptr; double *d_v = nullptr, *d_sum = nullptr;
     int rc = QBX_OK;
     do {

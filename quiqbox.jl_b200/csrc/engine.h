@@ -79,7 +79,8 @@ public:
     void release_store();
 
     static int synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_t seed, double *secs,
-                         double *checksum, int64_t nsample, double *sample_out, double *sample_geom, cudaStream_t s);
+                         double *checksum, double *prim_quartets, int64_t nsample, double *sample_out,
+                         double *sample_geom, cudaStream_t s);
 
 private:
     Engine() = default;

@@ -299,7 +299,7 @@ struct EriClass {
 // behind the few threads that drew a heavy task (it halved the throughput at 1/8 of the list,
 // i.e. on 8 GPUs); with the queue the light chunks at the end fill the tail.
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(QBX_ERI_THREADS) eri_class_kernel(ClassArgs p)
+__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA + LB + LC + LD <= 2 ? 3 : 1)) eri_class_kernel(ClassArgs p)
 {
     using EC = EriClass<LA, LB, LC, LD>;
     extern __shared__ double boys_smem[];

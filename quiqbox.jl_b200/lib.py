@@ -32,8 +32,8 @@ SIGNATURES = {
     "qbx_fock_build_device": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_one_body": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_boys": [C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
-    "qbx_prim_batch": [C.c_int] * 5 + [C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                        C.c_void_p],
+    "qbx_prim_batch": [C.c_int] * 5 + [C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p],
     "qbx_stats": [C.c_void_p, C.c_void_p, C.c_int],
 }
 

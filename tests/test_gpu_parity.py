@@ -225,11 +225,11 @@ def test_synthetic_class_batch_vs_oracle(cls):
     for K in (1, 3):
         nq, ns = 4096, 12
         ncomp = np.prod([(l + 1) * (l + 2) // 2 for l in cls])
-        secs, chk = C.c_double(), C.c_double()
+        secs, chk, npq = C.c_double(), C.c_double(), C.c_double()
         out = np.zeros((ns, ncomp)); geom = np.zeros((ns, 4, 3 + 2 * K))
-        L.check(L.load().qbx_prim_batch(la, lb, lc, ld, K, nq, 42, C.byref(secs), C.byref(chk), ns, L.ptr(out),
-                                        L.ptr(geom)))
-        assert secs.value > 0 and np.isfinite(chk.value)
+        L.check(L.load().qbx_prim_batch(la, lb, lc, ld, K, nq, 42, C.byref(secs), C.byref(chk), C.byref(npq), ns,
+                                        L.ptr(out), L.ptr(geom)))
+        assert secs.value > 0 and np.isfinite(chk.value) and 0 < npq.value <= nq * K ** 4
         for q in range(ns):
             sh = [[qb.GTO(tuple(geom[q, t, :3]), tuple(geom[q, t, 3:3 + K]), tuple(geom[q, t, 3 + K:]), ijk)
                    for ijk in qb.SubshellXYZs(l)] for t, l in enumerate(cls)]
