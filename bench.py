@@ -318,6 +318,13 @@ def main():
         kflops = cls[k, 4] / cls[k, 1] * 1e-12 if cls[k, 1] > 0 else 0.0
         all_flops = cls[:, 4].sum() / (eri_ms * 1e-3) * 1e-12       # all classes, overlapped, this rank
         digest_gbs = (info["stored_bytes"] / (fock_ms * 1e-3)) * 1e-9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj["workload"] == label and world == tj["n_gpus"]:
+                traffic = tj["dram_bytes_per_launch"].get(f"eri_class_kernel<{code // 1000},{code // 100 % 10},{code // 10 % 10},{code % 10}>")
+        except Exception:
+            pass
         per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
                       "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],
                       "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0} for r in cls if r[2] > 0]
@@ -333,7 +340,8 @@ def main():
             "gpu_launches": int(round((st1["launches"] - st0["launches"]))),
             "roofline": {"bound": "fp64", "kernel": f"eri_class_kernel<{code // 1000},{code // 100 % 10},{code // 10 % 10},{code % 10}>",
                          "achieved": kflops, "peak": peak.value, "unit": "TFLOP/s", "frac": kflops / peak.value if peak.value else None,
-                         "traffic": None, "peak_source": "measured in this run (qbx_fp64_peak, DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
+                         "traffic": traffic, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/traffic.json); the kernel is FP64-bound, its DRAM traffic is the packed output plus the task list",
+                         "peak_source": "measured in this run (qbx_fp64_peak, DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
                          "all_eri_kernels_achieved": all_flops, "all_eri_kernels_frac": all_flops / peak.value if peak.value else None,
                          "work_model": "SURVEY.md 8(d): flops = prim_quartets*(prim+acc) + quartets*hrr"},
             "roofline_digest": {"bound": "hbm", "kernel": "digest_kernel<*> (stored-mode Fock build)", "achieved": digest_gbs,
