@@ -339,6 +339,21 @@ def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=
             Gs = [comm.allreduce(G) for G in Gs]
         return Gs
 
-    Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCore(S, Hcore, gcore, Ns, config, None, printInfo)
+    def sad():
+        """Superposition of atomic densities, HartreeFock.jl:266-293: for every nucleus a UHF run
+        (:ADIIS to 1e-2, at most SADHFmaxStep = 50 steps, CoreH start) in the field of that nucleus
+        alone, with the whole system's occupation and two-electron integrals; the atomic densities
+        are summed and divided by the number of atoms."""
+        T = elecKinetics(basis)
+        ne_ab = (ne - ne // 2, ne // 2)
+        acfg = HFconfig(HF=UOHartreeFock(), initial=":CoreH", strategy=SCFconfig((":ADIIS",), (1e-2,)), maxStep=50)
+        Da, Db = np.zeros_like(S), np.zeros_like(S)
+        for sym, xyz in nucInfo:
+            Hatom = T + nucAttractions(NuclearCluster([sym], [xyz]), basis)
+            out = runHartreeFockCore(S, Hatom, gcore, ne_ab, acfg)
+            Da += out[1][0]; Db += out[1][1]
+        return Da / len(nucInfo), Db / len(nucInfo)
+
+    Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCore(S, Hcore, gcore, Ns, config, sad, printInfo)
     return HFfinalInfo((E, nucRepulsion(nucInfo)), Cs, Ds, Fs, tuple(eps), conv, steps, nb,
                        trace if config.saveTrace else trace[-1:])

@@ -328,3 +328,17 @@ def test_water16_full_size_properties():
         e[mode] = sum(r.energy)
     assert e["stored"] == pytest.approx(e["direct"], abs=1e-8)
     assert -1217.5 < e["stored"] < -1216.0                     # 16 x E(H2O/cc-pVDZ) = -1216.43 plus binding
+
+
+def test_sad_guess_and_default_config():
+    # runHartreeFock(nucInfo, bs) with the reference's defaults: RHF by electron count, initial = :SAD
+    # (HartreeFock.jl:266-293, 895-904), on H2O2/6-31G (HartreeFock-test.jl:306) and two H2 curve points (:266)
+    nuc, xyz = h2o2()
+    r = qb.runHartreeFock((nuc, xyz), mol_basis(nuc, xyz, "6-31G"))
+    assert r.converged and r.energy[0] == pytest.approx(-187.42063898359095, abs=2.5e-9)
+    g = json.load(open(os.path.join(HERE, "golden", "h2_321g_curve.json")))
+    for k in (7, 40):
+        nuc, xyz = h2(0.1 + 0.2 * k)
+        for hf, key in ((qb.RCHartreeFock(), "rhfs"), (qb.UOHartreeFock(), "uhfs")):
+            r = qb.runHartreeFock((nuc, xyz), mol_basis(nuc, xyz, "3-21G"), qb.HFconfig(HF=hf, initial=":SAD", maxStep=300))
+            assert sum(r.energy) == pytest.approx(g[key][k], abs=7.5e-7), (k, key)

@@ -149,3 +149,29 @@ def test_h2o2_631g():
     # HartreeFock-test.jl:294-352
     (_, _, _, _, E, conv, *_), _, _ = _scf(*h2o2(), "6-31G", "RHF", thr=5e-10)
     assert conv and E == pytest.approx(-187.42063898359095, abs=2.5e-9)
+
+
+def test_h2o2_631g_default_config_sad_guess():
+    # HartreeFock-test.jl:306 (HFc0 = HFconfig(Float64): initial = :SAD, default SCF stages) and :309 (HFc1)
+    from quiqbox_b200.hartreefock import HFconfig, SCFconfig, UOHartreeFock, runHartreeFockCore
+    nuc, xyz = h2o2()
+    cl = qb.NuclearCluster(nuc, xyz)
+    bs = sum((qb.genGaussTypeOrbSeq(c, s, "6-31G") for s, c in zip(nuc, xyz)), [])
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs))
+    S, T = ob.one_body("overlap"), ob.one_body("kinetic")
+    H = T + ob.one_body("nuclear", cl.charges, cl.coordArray)
+    g = oracle.gcore_from_tensor(ob.eri_tensor())
+    ne = int(cl.charges.sum())
+
+    def sad():                                            # HartreeFock.jl:266-293
+        acfg = HFconfig(HF=UOHartreeFock(), initial=":CoreH", strategy=SCFconfig((":ADIIS",), (1e-2,)), maxStep=50)
+        Da, Db = np.zeros_like(S), np.zeros_like(S)
+        for sym, x in cl:
+            Ha = T + ob.one_body("nuclear", [qb.basis.NuclearChargeDict[sym]], [x])
+            out = runHartreeFockCore(S, Ha, g, (ne - ne // 2, ne // 2), acfg)
+            Da += out[1][0]; Db += out[1][1]
+        return Da / len(cl), Db / len(cl)
+
+    for cfg in (HFconfig(), HFconfig(initial=":SAD", strategy=SCFconfig(threshold=5e-10, secondaryConvRatio=(5, 5)))):
+        out = runHartreeFockCore(S, H, g, (ne // 2,), cfg, sad)
+        assert out[5] and out[4] == pytest.approx(-187.42063898359095, abs=2.5e-9)
