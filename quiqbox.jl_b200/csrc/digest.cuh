@@ -55,9 +55,10 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
     if (blk >= nblk) return;
     const int64_t q0 = blk * 128 + threadIdx.x;
     if (q0 - (threadIdx.x & 31) >= p.ntasks) return;          // whole warp past the end
-    const bool valid = q0 < p.ntasks;
-    const int64_t q = valid ? q0 : p.ntasks - 1;
-    const int2 t = p.tasks[q];
+    const int64_t q = q0 < p.ntasks ? q0 : p.ntasks - 1;
+    int2 t = p.tasks[q];
+    const bool valid = q0 < p.ntasks && t.y >= 0;              // ket = -1: unused slot of a group task
+    if (t.y < 0) t.y = 0;
     const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);   // (shell A, shell B, first A, first B)
     double f = valid ? 1.0 : 0.0;
     if (rb.x == rb.y) f *= 0.5;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(128) scatter_kernel(ScatterArgs p)
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= p.ntasks) return;
     const int2 t = p.tasks[q];
+    if (t.y < 0) return;
     const int2 sb = p.bra_shells[t.x], sk = p.ket_shells[t.y];
     const int64_t N = p.nbf;
     double *T = p.tensor;

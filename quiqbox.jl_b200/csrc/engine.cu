@@ -403,6 +403,11 @@ int Engine::upload(bool pair_adjacent)
             for (int i = 0; i < P.npair; ++i) info[i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
             QBX_CUDA(cudaMalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
             if (P.npair) QBX_CUDA(cudaMemcpy(P.info, info.data(), info.size() * sizeof(int4), cudaMemcpyHostToDevice));
+            // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
+            if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
+                if ((rc = qbx_group_build(shells_, sh, groups_))) return rc;
+                use_groups_ = groups_.ng > 0 && groups_.ng < P.npair;     // only when something is shared
+            }
         }
     }
     QBX_CUDA(cudaEventCreate(&ev0_));
@@ -413,6 +418,7 @@ int Engine::upload(bool pair_adjacent)
 Engine::~Engine()
 {
     release_store();
+    qbx_group_free(groups_);
     for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); cudaFree(p.info); }
     cudaFree(d_shell_bf_); cudaFree(d_shell_scale_); cudaFree(d_shell_first_); cudaFree(d_ext_of_int_); cudaFree(d_Dint_);
     cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_); cudaFree(d_counters_);
@@ -428,7 +434,8 @@ void Engine::release_store()
 {
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
-            cudaFree(tasks_[b][k].tasks); tasks_[b][k] = TaskList();
+            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].gt_bra); cudaFree(tasks_[b][k].gt_grp); cudaFree(tasks_[b][k].gt_off);
+            tasks_[b][k] = TaskList();
             cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
         }
     mode_ = -1;
@@ -452,11 +459,8 @@ void Engine::info(int64_t *info) const
 }
 
 // ------------------------------------------------------------------ ERI launches
-int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s)
+int Engine::eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a)
 {
-    const ClassOps *ops = qbx_class_ops(bc, kc);
-    if (!ops) { qbx_set_error("internal: no kernel for this class"); return QBX_ERR_STATE; }
-    ClassArgs a;
     a.bra = pairs_[bc].view(); a.ket = pairs_[kc].view();
     a.tasks = tasks; a.ntasks = n; a.out = out;
     a.shell_scale = d_shell_scale_;
@@ -465,6 +469,16 @@ int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, c
     a.counter = d_counters_ + counter_next_;
     counter_next_ = (counter_next_ + 1) % 1024;
     QBX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), s));
+    return QBX_OK;
+}
+
+int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s)
+{
+    const ClassOps *ops = qbx_class_ops(bc, kc);
+    if (!ops) { qbx_set_error("internal: no kernel for this class"); return QBX_ERR_STATE; }
+    ClassArgs a;
+    int rc0 = eri_args(bc, kc, tasks, n, out, s, a);
+    if (rc0) return rc0;
     // Large classes (>= coop_min contracted accumulators per quartet) go to the warp-cooperative
     // kernel; QBX_COOP_MIN_ACC overrides the threshold (0 = every class, for tests).
     static const int coop_min = std::min(QBX_COOP_ACC, getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : QBX_COOP_ACC);
@@ -520,6 +534,7 @@ int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskLi
     for (int64_t c = rank; c < nfull; c += nranks) mine += QBX_TASK_CHUNK;
     if (rem && nfull % nranks == rank) mine += rem;
     out.n = mine;
+    out.nvalid = mine;
     if (mine == 0) return QBX_OK;
     int64_t *d_off = nullptr;
     QBX_CUDA(cudaMalloc(&d_off, rowoff.size() * sizeof(int64_t)));
@@ -574,14 +589,18 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
     if (rc) return rc;
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc) {
-            if ((rc = build_tasks(bc, kc, tol, rank, nranks, tasks_[bc][kc], s))) return rc;
+            if (mode == 0 && grouped(bc, kc))
+                rc = qbx_group_tasks(groups_, pairs_[bc], pairs_[kc], bc == kc, tol, rank, nranks, tasks_[bc][kc], s);
+            else
+                rc = build_tasks(bc, kc, tol, rank, nranks, tasks_[bc][kc], s);
+            if (rc) return rc;
             const ClassOps *ops = qbx_class_ops(bc, kc);
             const TaskList &tl = tasks_[bc][kc];
-            n_quartets_ += tl.n;
-            n_values_ += tl.n * ops->ncomp;
+            n_quartets_ += tl.nvalid;
+            n_values_ += tl.nvalid * ops->ncomp;
             n_primq_ += tl.nprimq;
             model_flops_ += tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
-                            (double)tl.n * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
+                            (double)tl.nvalid * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
             if (mode == 0 && tl.n > 0) {
                 const size_t bytes = (size_t)tl.n * ops->ncomp * sizeof(double);
                 if (cudaMalloc(&vals_[bc][kc], bytes) != cudaSuccess) {
@@ -646,7 +665,15 @@ int Engine::recompute(cudaStream_t s, double *stats, bool timed)
             }
             const TaskList &tl = tasks_[bc][kc];
             if (tl.n == 0) continue;
-            if ((rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], timed ? s : side_[k++ % kSide]))) return rc;
+            cudaStream_t cs = timed ? s : side_[k++ % kSide];
+            if (tl.ngt > 0) {
+                ClassArgs a;
+                if ((rc = eri_args(bc, kc, tl.tasks, tl.n, vals_[bc][kc], cs, a))) return rc;
+                rc = qbx_group_eri(kClsLa[bc], groups_, a, tl, cs);
+            } else {
+                rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], cs);
+            }
+            if (rc) return rc;
             stats[0] += 1;
         }
     if (timed) {
@@ -674,11 +701,11 @@ int Engine::class_stats(cudaStream_t s, double *stats, double *out)
             double *o = out + 6 * c;
             o[0] = ops->la * 1000 + ops->lb * 100 + ops->lc * 10 + ops->ld;
             o[1] = ms * 1e-3;
-            o[2] = (double)tl.n;
+            o[2] = (double)tl.nvalid;
             o[3] = tl.nprimq;
             o[4] = tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
-                   (double)tl.n * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
-            o[5] = (double)tl.n * ops->ncomp;
+                   (double)tl.nvalid * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
+            o[5] = (double)tl.nvalid * ops->ncomp;
         }
     return QBX_OK;
 }

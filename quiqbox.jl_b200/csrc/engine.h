@@ -58,10 +58,28 @@ struct DevPairSet {
 };
 
 struct TaskList {
-    int2 *tasks = nullptr;
-    int64_t n = 0;
+    int2 *tasks = nullptr;               // (bra pair, ket pair); ket = -1 marks an unused slot of a group task
+    int64_t n = 0;                       // slots
+    int64_t nvalid = 0;                  // real quartets among them
     double nprimq = 0;                   // primitive quartets behind these tasks
+    // group tasks (eri_group.cu): task t covers the slots gt_off[t] .. gt_off[t] + nmem(gt_grp[t]) - 1
+    int ngt = 0;
+    int *gt_bra = nullptr, *gt_grp = nullptr, *gt_off = nullptr;
 };
+
+// (ss) group pairs: ket-side general-contraction sharing, see eri_group.cu
+struct GroupSet {
+    int ng = 0;
+    int *nmem = nullptr, *members = nullptr, *prim_off = nullptr;
+    double *soa = nullptr;
+    int2 *soa_idx = nullptr;
+    std::vector<int> h_nprim, h_nmem;
+};
+int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out);
+void qbx_group_free(GroupSet &g);
+int qbx_group_tasks(const GroupSet &G, const struct DevPairSet &B, const struct DevPairSet &K, bool same, double tol, int rank,
+                    int nranks, TaskList &tl, cudaStream_t s);
+int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList &tl, cudaStream_t s);
 
 class Engine {
 public:
@@ -88,6 +106,10 @@ private:
     int ensure_schwarz(cudaStream_t s);
     int build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s);
     int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s);
+    int eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a);
+    bool grouped(int bc, int kc) const { return use_groups_ && kc == 0 && (bc == 0 || bc == 1); }   // (ss|ss), (ps|ss); (ds|ss) measured slower
+    GroupSet groups_;
+    bool use_groups_ = false;
 
     std::vector<HostShell> shells_;
     int64_t nbf_ = 0;

@@ -293,7 +293,7 @@ struct EriClass {
 #define QBX_ERI_THREADS 256
 
 // Persistent blocks: the Boys columns of this class are staged in shared memory once, then
-// the block pulls chunks of 256 consecutive tasks from a global work queue.  The list is
+// its warps pull chunks of 32 consecutive tasks from a global work queue.  The list is
 // ordered heavy-first (rows by bra contraction length, kets likewise), and a single task spans
 // 1 to 6561 primitive quartets, so a static grid-stride assignment leaves most of the GPU idle
 // behind the few threads that drew a heavy task (it halved the throughput at 1/8 of the list,
@@ -303,16 +303,18 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA + LB + LC + LD <= 2 ? 3 :
 {
     using EC = EriClass<LA, LB, LC, LD>;
     extern __shared__ double boys_smem[];
-    __shared__ unsigned int s_chunk;
     boys_stage_smem<EC::L>(p.boys, boys_smem);
-    const int64_t nchunk = (p.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    __syncthreads();
+    // every WARP pulls its own 32-task chunks: a block-wide queue needs a barrier per chunk, and
+    // the warps then wait for the slowest task of the block (ncu: 5 of 9 stall cycles per issue)
+    const int64_t nchunk = (p.ntasks + 31) / 32;
+    const int lane = threadIdx.x & 31;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_chunk = atomicAdd(p.counter, 1u);
-        __syncthreads();
-        const int64_t chunk = s_chunk;
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(p.counter, 1u);
+        const int64_t chunk = __shfl_sync(0xffffffffu, c, 0);
         if (chunk >= nchunk) break;
-        const int64_t q = chunk * QBX_ERI_THREADS + threadIdx.x;
+        const int64_t q = chunk * 32 + lane;
         if (q >= p.ntasks) continue;
         const int2 t = p.tasks[q];
         const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;

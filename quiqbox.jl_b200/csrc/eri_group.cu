@@ -1,0 +1,419 @@
+// General-contraction sharing on the ket side of the (xs|ss) classes.
+//
+// cc-pVDZ-type basis sets build several contracted s functions from ONE primitive set (O: two
+// 9-term s shells and a 1-term one on the same 9 exponents; H: 4 + 1 on 4).  The reference
+// exploits this by de-duplicating primitives (indexGetOrbCore!, src/OrbitalBases.jl:337-365) and
+// memoising primitive integrals (TwoBodyIntegralValCache, src/Integration/Framework.jl:68-89).
+// Here the s shells of one centre that share exponents form a primitive GROUP; a ket "group
+// pair" (P,Q) stands for all its member shell pairs (up to 3 x 3 = 9), the primitive integrals
+// over P x Q are evaluated once per bra pair and contracted with the members' coefficient
+// products.  (ss|ss), (ps|ss) and (ds|ss) are 49 % of the (H2O)16 ERI time; for O-O kets this cuts
+// the primitive work 361 -> 81.
+//
+// Everything downstream (packed store, digestion, scatter) keeps seeing ordinary tasks: the task
+// list of such a class is laid out group task by group task, one slot per member, and slots of
+// members that are screened out or violate the bra >= ket uniqueness rule carry ket = -1.
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#include "engine.h"
+
+#define QBX_GRP_MAXMEM 9
+#define QBX_GRP_NF (5 + QBX_GRP_MAXMEM)      // eta, Qx, Qy, Qz, Kgeom, cc[9]
+#define QBX_GRP_CHUNK 64                     // sharding granule in group tasks
+
+namespace {
+
+// ------------------------------------------------------------------ task building
+__device__ __forceinline__ bool member_ok(int j, int i, int same, double qi, const double *Qk, double tol)
+{
+    return j >= 0 && (!same || j <= i) && qi * Qk[j] >= tol;
+}
+
+__global__ void k_gcount(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
+                         int *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const double qi = Qb[i];
+    int c = 0;
+    for (int g = 0; g < ng; ++g) {
+        bool any = false;
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
+        c += any;
+    }
+    cnt[i] = c;
+}
+
+__global__ void k_gcount_owned(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
+                               const int *nmem, const int64_t *growoff, int rank, int nranks, int *cnt_tasks, int *cnt_slots)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const double qi = Qb[i];
+    int64_t idx = growoff[i];
+    int ct = 0, cs = 0;
+    for (int g = 0; g < ng; ++g) {
+        bool any = false;
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
+        if (!any) continue;
+        if ((idx / QBX_GRP_CHUNK) % nranks == rank) { ++ct; cs += nmem[g]; }
+        ++idx;
+    }
+    cnt_tasks[i] = ct;
+    cnt_slots[i] = cs;
+}
+
+__global__ void k_gfill(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
+                        const int *nmem, const int64_t *growoff, int rank, int nranks, const int64_t *toff,
+                        const int64_t *soff, int *gt_bra, int *gt_grp, int *gt_off, int2 *tasks)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const double qi = Qb[i];
+    int64_t idx = growoff[i], t = toff[i], s = soff[i];
+    for (int g = 0; g < ng; ++g) {
+        bool any = false;
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
+        if (!any) continue;
+        if ((idx / QBX_GRP_CHUNK) % nranks == rank) {
+            gt_bra[t] = i; gt_grp[t] = g; gt_off[t] = (int)s;
+            for (int m = 0; m < nmem[g]; ++m) {
+                const int j = members[g * QBX_GRP_MAXMEM + m];
+                tasks[s + m] = make_int2(i, member_ok(j, i, same, qi, Qk, tol) ? j : -1);
+            }
+            ++t; s += nmem[g];
+        }
+        ++idx;
+    }
+}
+
+__global__ void k_gstats(const int2 *tasks, int64_t nslots, const int *gt_bra, const int *gt_grp, int ntasks,
+                         const int *poffb, const int *poffg, double *out /*[2]: valid slots, prim quartets*/)
+{
+    __shared__ double r0[256], r1[256];
+    double a = 0, b = 0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nslots; q += (int64_t)gridDim.x * blockDim.x) a += tasks[q].y >= 0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < ntasks; q += (int64_t)gridDim.x * blockDim.x)
+        b += (double)(poffb[gt_bra[q] + 1] - poffb[gt_bra[q]]) * (double)(poffg[gt_grp[q] + 1] - poffg[gt_grp[q]]);
+    r0[threadIdx.x] = a; r1[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { r0[threadIdx.x] += r0[threadIdx.x + s]; r1[threadIdx.x] += r1[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(out, r0[0]); atomicAdd(out + 1, r1[0]); }
+}
+
+// ------------------------------------------------------------------ the ERI kernel
+struct GroupArgs {
+    PairSet bra, ket;          // ket = the regular (ss) pair set (member shells -> weights)
+    const int2 *tasks;         // slots
+    int64_t nslots;
+    const int *gt_bra, *gt_grp, *gt_off;
+    int ntasks;
+    const int *grp_nmem, *grp_prim_off;
+    const double *grp_soa;
+    const int2 *grp_soa_idx;
+    double *out;
+    const double *shell_scale;
+    BoysTable boys;
+    unsigned int *counter;
+};
+
+template <int LA>
+__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_kernel(GroupArgs p)
+{
+    using EC = EriClass<LA, 0, 0, 0>;
+    constexpr int NA = NC(LA);
+    extern __shared__ double boys_smem[];
+    boys_stage_smem<EC::L>(p.boys, boys_smem);
+    __syncthreads();
+    const int nchunk = (p.ntasks + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    for (;;) {                                               // per-warp work queue, see eri_class.cuh
+        unsigned int cq = 0;
+        if (lane == 0) cq = atomicAdd(p.counter, 1u);
+        const int chunk = (int)__shfl_sync(0xffffffffu, cq, 0);
+        if (chunk >= nchunk) break;
+        const int t = chunk * 32 + lane;
+        if (t >= p.ntasks) continue;
+        const int ib = p.gt_bra[t], g = p.gt_grp[t], off = p.gt_off[t];
+        const double *gb = p.bra.geom + 8 * (int64_t)ib;
+        const double A[3] = {gb[0], gb[1], gb[2]};
+        const int pb0 = p.bra.prim_off[ib], pb1 = p.bra.prim_off[ib + 1];
+        const int nk = p.grp_prim_off[g + 1] - p.grp_prim_off[g];
+        const int2 si = p.grp_soa_idx[g];
+        double acc[QBX_GRP_MAXMEM][NA];
+#pragma unroll
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m)
+#pragma unroll
+            for (int c = 0; c < NA; ++c) acc[m][c] = 0.0;
+        const double zero3[3] = {0.0, 0.0, 0.0};
+        const int nmem = p.grp_nmem[g];
+        // ket primitive outermost: its record and the members' coefficient products are loaded once,
+        // the (warp-uniform) bra primitives run inside, and the coefficient contraction happens once
+        // per ket primitive instead of once per primitive quartet
+        const double *kp = p.grp_soa + si.x;
+        for (int pk = 0; pk < nk; ++pk, kp += QBX_GRP_NF * si.y) {
+            const double eta = __ldg(kp);
+            const double Q[3] = {__ldg(kp + si.y), __ldg(kp + 2 * si.y), __ldg(kp + 3 * si.y)};
+            const double Kg = __ldg(kp + 4 * si.y);
+            double v[NA];
+#pragma unroll
+            for (int c = 0; c < NA; ++c) v[c] = 0.0;
+            for (int pb = pb0; pb < pb1; ++pb) {
+                const double4 b0 = ldg4(p.bra.prim + 8 * (int64_t)pb);
+                const double4 b1 = ldg4(p.bra.prim + 8 * (int64_t)pb + 4);
+                const double P[3] = {b0.y, b0.z, b0.w};
+                const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+                EC::primitive(v, boys_smem, b0.x, P, b1.x, PA, b1.z, zero3, eta, Q, Kg, 0.0, zero3);
+            }
+#pragma unroll
+            for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
+                if (m < nmem) {
+                    const double cc = __ldg(kp + (5 + m) * si.y);
+#pragma unroll
+                    for (int c = 0; c < NA; ++c) acc[m][c] = fma(cc, v[c], acc[m][c]);
+                }
+            }
+        }
+        const int2 sb = p.bra.shells[ib];
+        const double *sA = p.shell_scale + 6 * sb.x;
+        const double sB = p.shell_scale[6 * sb.y];
+#pragma unroll
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
+            if (m >= nmem) break;
+            const int j = p.tasks[off + m].y;
+            double w = 0.0;
+            if (j >= 0) {
+                const int2 sk = p.ket.shells[j];
+                w = sB * p.shell_scale[6 * sk.x] * p.shell_scale[6 * sk.y];
+            }
+#pragma unroll
+            for (int c = 0; c < NA; ++c) p.out[(int64_t)c * p.nslots + off + m] = acc[m][c] * sA[c] * w;
+        }
+    }
+}
+
+template <int LA>
+int launch_group(const GroupArgs &a, cudaStream_t s)
+{
+    static int max_blocks = 0;
+    if (max_blocks == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        QBX_CUDA(cudaGetDevice(&dev));
+        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_group_kernel<LA>, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES));
+        max_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int need = (a.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    eri_group_kernel<LA><<<need < max_blocks ? need : max_blocks, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+// Primitive groups of the s shells and the (ss) group pairs.  `ss_pairs` = shells of every
+// regular (ss) pair in the order of the device pair set.
+int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out)
+{
+    // 1. primitive groups: s shells on one centre whose exponents are a subset of the group's
+    struct PG { double cen[3]; std::vector<double> xpn; std::vector<int> shells; };
+    std::vector<PG> pgs;
+    std::vector<int> pg_of(sh.size(), -1);
+    std::vector<std::vector<double>> coef(sh.size());         // per shell, over its group's primitives
+    for (size_t s = 0; s < sh.size(); ++s) {
+        if (sh[s].l != 0) continue;
+        int found = -1;
+        for (size_t g = 0; g < pgs.size() && found < 0; ++g) {
+            PG &G = pgs[g];
+            if (G.shells.size() >= 3 || G.cen[0] != sh[s].cen[0] || G.cen[1] != sh[s].cen[1] || G.cen[2] != sh[s].cen[2]) continue;
+            bool sub = true;
+            for (double x : sh[s].xpn) sub &= std::find(G.xpn.begin(), G.xpn.end(), x) != G.xpn.end();
+            if (sub) found = (int)g;
+        }
+        if (found < 0) {
+            PG G;
+            for (int d = 0; d < 3; ++d) G.cen[d] = sh[s].cen[d];
+            G.xpn = sh[s].xpn;                               // shells come longest contraction first
+            pgs.push_back(G);
+            found = (int)pgs.size() - 1;
+        }
+        PG &G = pgs[found];
+        G.shells.push_back((int)s);
+        pg_of[s] = found;
+        coef[s].assign(G.xpn.size(), 0.0);
+        for (size_t k = 0; k < sh[s].xpn.size(); ++k) {
+            const size_t pos = std::find(G.xpn.begin(), G.xpn.end(), sh[s].xpn[k]) - G.xpn.begin();
+            coef[s][pos] += sh[s].coef[k];
+        }
+    }
+    // 2. group pairs and their members (regular pair indices)
+    std::map<std::pair<int, int>, int> gp_index;
+    std::vector<std::vector<int>> members;
+    std::vector<std::pair<int, int>> gp_pq;
+    for (size_t j = 0; j < ss_pairs.size(); ++j) {
+        int P = pg_of[ss_pairs[j].x], Q = pg_of[ss_pairs[j].y];
+        if (P < Q) std::swap(P, Q);
+        auto it = gp_index.find({P, Q});
+        if (it == gp_index.end()) {
+            it = gp_index.emplace(std::make_pair(P, Q), (int)members.size()).first;
+            members.emplace_back();
+            gp_pq.push_back({P, Q});
+        }
+        members[it->second].push_back((int)j);
+    }
+    const size_t ng0 = members.size();
+    for (auto &m : members)
+        if (m.size() > QBX_GRP_MAXMEM) { qbx_set_error("internal: group pair with more than 9 members"); return QBX_ERR_STATE; }
+    // 3. primitive pairs of each group pair: geometry + the members' coefficient products
+    struct Rec { double v[QBX_GRP_NF]; };
+    std::vector<std::vector<Rec>> prims(ng0);
+    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
+    for (size_t g = 0; g < ng0; ++g) {
+        const PG &P = pgs[gp_pq[g].first], &Q = pgs[gp_pq[g].second];
+        double pq2 = 0;
+        for (int d = 0; d < 3; ++d) pq2 += (P.cen[d] - Q.cen[d]) * (P.cen[d] - Q.cen[d]);
+        for (size_t a = 0; a < P.xpn.size(); ++a)
+            for (size_t b = 0; b < Q.xpn.size(); ++b) {
+                const double x = P.xpn[a], y = Q.xpn[b], z = x + y;
+                Rec r;
+                r.v[0] = z;
+                for (int d = 0; d < 3; ++d) r.v[1 + d] = (x * P.cen[d] + y * Q.cen[d]) / z;
+                r.v[4] = pref * exp(-x * y / z * pq2) / z;
+                double big = 0;
+                for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
+                    double cc = 0.0;
+                    if (m < (int)members[g].size()) {
+                        const int2 cd = ss_pairs[members[g][m]];
+                        // member (C,D): C may belong to P or to Q
+                        if (pg_of[cd.x] == gp_pq[g].first) cc = coef[cd.x][a] * coef[cd.y][b];
+                        else cc = coef[cd.y][a] * coef[cd.x][b];
+                    }
+                    r.v[5 + m] = cc;
+                    big = std::max(big, fabs(cc * r.v[4]));
+                }
+                if (big < 1e-24) continue;
+                prims[g].push_back(r);
+            }
+    }
+    // 4. order groups by primitive count (descending, stable) and upload
+    std::vector<int> order(ng0);
+    for (size_t g = 0; g < ng0; ++g) order[g] = (int)g;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prims[x].size() > prims[y].size(); });
+    out.ng = (int)ng0;
+    out.h_nprim.resize(ng0); out.h_nmem.resize(ng0);
+    std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0);
+    for (size_t n = 0; n < ng0; ++n) {
+        const int g = order[n];
+        out.h_nprim[n] = (int)prims[g].size();
+        out.h_nmem[n] = (int)members[g].size();
+        for (size_t m = 0; m < members[g].size(); ++m) mem[n * QBX_GRP_MAXMEM + m] = members[g][m];
+        poff[n + 1] = poff[n] + (int)prims[g].size();
+    }
+    std::vector<double> soa((size_t)QBX_GRP_NF * poff.back(), 0.0);
+    std::vector<int2> soa_idx(ng0);
+    size_t base = 0, g0 = 0;
+    while (g0 < ng0) {
+        size_t g1 = g0;
+        while (g1 < ng0 && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
+        const size_t gs = g1 - g0, np = (size_t)out.h_nprim[g0];
+        for (size_t n = g0; n < g1; ++n) {
+            soa_idx[n] = make_int2((int)(base + (n - g0)), (int)gs);
+            for (size_t pp = 0; pp < np; ++pp)
+                for (int k = 0; k < QBX_GRP_NF; ++k) soa[base + (pp * QBX_GRP_NF + k) * gs + (n - g0)] = prims[order[n]][pp].v[k];
+        }
+        base += gs * np * QBX_GRP_NF;
+        g0 = g1;
+    }
+    QBX_CUDA(cudaMalloc(&out.nmem, std::max<size_t>(1, ng0) * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&out.members, std::max<size_t>(1, mem.size()) * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
+    QBX_CUDA(cudaMalloc(&out.soa_idx, std::max<size_t>(1, ng0) * sizeof(int2)));
+    if (ng0) {
+        QBX_CUDA(cudaMemcpy(out.nmem, out.h_nmem.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice));
+        QBX_CUDA(cudaMemcpy(out.members, mem.data(), mem.size() * sizeof(int), cudaMemcpyHostToDevice));
+        QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), ng0 * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    QBX_CUDA(cudaMemcpy(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!soa.empty()) QBX_CUDA(cudaMemcpy(out.soa, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return QBX_OK;
+}
+
+void qbx_group_free(GroupSet &g)
+{
+    cudaFree(g.nmem); cudaFree(g.members); cudaFree(g.prim_off); cudaFree(g.soa); cudaFree(g.soa_idx);
+    g = GroupSet();
+}
+
+// Builds the slot list (tl.tasks / tl.n) and the group tasks of one (x s|ss) class for this rank.
+int qbx_group_tasks(const GroupSet &G, const DevPairSet &B, const DevPairSet &K, bool same, double tol, int rank, int nranks,
+                    TaskList &tl, cudaStream_t s)
+{
+    tl = TaskList();
+    if (B.npair == 0 || G.ng == 0) return QBX_OK;
+    const int nb = B.npair, grid = (nb + 127) / 128;
+    int *d_c0 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
+    int64_t *d_o0 = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
+    QBX_CUDA(cudaMalloc(&d_c0, nb * sizeof(int))); QBX_CUDA(cudaMalloc(&d_c1, nb * sizeof(int))); QBX_CUDA(cudaMalloc(&d_c2, nb * sizeof(int)));
+    QBX_CUDA(cudaMalloc(&d_o0, (nb + 1) * sizeof(int64_t))); QBX_CUDA(cudaMalloc(&d_o1, (nb + 1) * sizeof(int64_t)));
+    QBX_CUDA(cudaMalloc(&d_o2, (nb + 1) * sizeof(int64_t)));
+    std::vector<int> c0(nb), c1(nb), c2(nb);
+    std::vector<int64_t> o0(nb + 1, 0), o1(nb + 1, 0), o2(nb + 1, 0);
+    k_gcount<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, d_c0);
+    QBX_CUDA(cudaMemcpyAsync(c0.data(), d_c0, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < nb; ++i) o0[i + 1] = o0[i] + c0[i];
+    QBX_CUDA(cudaMemcpyAsync(d_o0, o0.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    k_gcount_owned<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, d_o0, rank, nranks, d_c1, d_c2);
+    QBX_CUDA(cudaMemcpyAsync(c1.data(), d_c1, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaMemcpyAsync(c2.data(), d_c2, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < nb; ++i) { o1[i + 1] = o1[i] + c1[i]; o2[i + 1] = o2[i] + c2[i]; }
+    tl.ngt = (int)o1[nb];
+    tl.n = o2[nb];
+    if (tl.ngt > 0) {
+        QBX_CUDA(cudaMemcpyAsync(d_o1, o1.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaMemcpyAsync(d_o2, o2.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaMalloc(&tl.tasks, tl.n * sizeof(int2)));
+        QBX_CUDA(cudaMalloc(&tl.gt_bra, tl.ngt * sizeof(int)));
+        QBX_CUDA(cudaMalloc(&tl.gt_grp, tl.ngt * sizeof(int)));
+        QBX_CUDA(cudaMalloc(&tl.gt_off, tl.ngt * sizeof(int)));
+        k_gfill<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, d_o0, rank, nranks, d_o1, d_o2,
+                                     tl.gt_bra, tl.gt_grp, tl.gt_off, tl.tasks);
+        QBX_CUDA(cudaGetLastError());
+        double *d_st = nullptr, st[2] = {0, 0};
+        QBX_CUDA(cudaMalloc(&d_st, 2 * sizeof(double)));
+        QBX_CUDA(cudaMemsetAsync(d_st, 0, 2 * sizeof(double), s));
+        k_gstats<<<296, 256, 0, s>>>(tl.tasks, tl.n, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, d_st);
+        QBX_CUDA(cudaMemcpyAsync(st, d_st, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        QBX_CUDA(cudaStreamSynchronize(s));
+        cudaFree(d_st);
+        tl.nvalid = (int64_t)st[0];
+        tl.nprimq = st[1];
+    }
+    cudaFree(d_c0); cudaFree(d_c1); cudaFree(d_c2); cudaFree(d_o0); cudaFree(d_o1); cudaFree(d_o2);
+    return QBX_OK;
+}
+
+int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList &tl, cudaStream_t s)
+{
+    if (tl.ngt <= 0) return QBX_OK;
+    GroupArgs g;
+    g.bra = a.bra; g.ket = a.ket; g.tasks = tl.tasks; g.nslots = tl.n;
+    g.gt_bra = tl.gt_bra; g.gt_grp = tl.gt_grp; g.gt_off = tl.gt_off; g.ntasks = tl.ngt;
+    g.grp_nmem = G.nmem; g.grp_prim_off = G.prim_off; g.grp_soa = G.soa; g.grp_soa_idx = G.soa_idx;
+    g.out = a.out; g.shell_scale = a.shell_scale; g.boys = a.boys; g.counter = a.counter;
+    switch (la) {
+    case 0: return launch_group<0>(g, s);
+    case 1: return launch_group<1>(g, s);
+    case 2: return launch_group<2>(g, s);
+    }
+    qbx_set_error("internal: no group kernel for this class");
+    return QBX_ERR_STATE;
+}
