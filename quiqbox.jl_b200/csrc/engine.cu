@@ -10,6 +10,11 @@
 #include <numeric>
 #include <random>
 #include <stdlib.h>
+#include <thrust/execution_policy.h>
+#include <thrust/functional.h>
+#include <thrust/sequence.h>
+#include <thrust/sort.h>
+#include <thrust/binary_search.h>
 
 // ------------------------------------------------------------------ class registry
 #define QBX_DECL(a, b, c, d) extern const ClassOps qbx_ops_##a##b##c##d;
@@ -116,10 +121,10 @@ __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk
     cnt[i] = c;
 }
 
-// Sharding granule: rank r owns chunks r, r + nranks, ...  One chunk = one ERI block (256 tasks).
+// Sharding granule: rank r owns chunks r, r + nranks, ...  One chunk = one warp's worth of tasks.
 // It must be much shorter than a bra row (up to ~6000 kets whose cost falls 81-fold along the
 // row): with 4096-task chunks the round-robin aliased with the rows and rank 0 was 2x slower.
-#define QBX_TASK_CHUNK 256
+#define QBX_TASK_CHUNK 32
 // one warp per bra row: compact the surviving kets in order; keep the chunks of this rank
 __global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol,
                              const int64_t *rowoff, int rank, int nranks, int2 *tasks)
@@ -182,6 +187,22 @@ __global__ void k_permute_in(int64_t Next, int64_t Nint, const int *ext_of_int, 
     Dint[e] = (i >= 0 && j >= 0) ? Dext[i + Next * j] : 0.0;
 }
 
+// cost of every 32-task chunk = primitive quartets behind its tasks
+__global__ void k_chunk_cost(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poffb,
+                             const int *poffk, float *cost)
+{
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;       // blockDim multiple of 32
+    float c = 0.f;
+    if (q < n) {
+        int b, k;
+        if (tasks) { b = tasks[q].x; k = tasks[q].y; } else { b = gt_bra[q]; k = gt_grp[q]; }
+        if (k >= 0) c = (float)(poffb[b + 1] - poffb[b]) * (float)(poffk[k + 1] - poffk[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));   // a warp runs at its slowest lane
+    if ((threadIdx.x & 31) == 0 && q < n + 31) cost[q / 32] = c;
+}
+
 __global__ void k_sum(const double *v, int64_t n, double *sum)
 {
     __shared__ double red[256];
@@ -197,6 +218,28 @@ __global__ void k_sum(const double *v, int64_t n, double *sum)
 }
 
 }  // namespace
+
+int qbx_chunk_order(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poff_bra,
+                    const int *poff_ket, int **order_out, int *nheavy_out, cudaStream_t s)
+{
+    *order_out = nullptr;
+    if (nheavy_out) *nheavy_out = 0;
+    const int64_t nchunk = (n + 31) / 32;
+    if (nchunk <= 1) return QBX_OK;
+    float *cost = nullptr;
+    QBX_CUDA(cudaMalloc(&cost, nchunk * sizeof(float)));
+    QBX_CUDA(cudaMalloc(order_out, nchunk * sizeof(int)));
+    const int64_t threads = nchunk * 32;
+    k_chunk_cost<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(tasks, gt_bra, gt_grp, n, poff_bra, poff_ket, cost);
+    QBX_CUDA(cudaGetLastError());
+    thrust::sequence(thrust::cuda::par.on(s), *order_out, *order_out + nchunk);
+    thrust::stable_sort_by_key(thrust::cuda::par.on(s), cost, cost + nchunk, *order_out, thrust::greater<float>());
+    if (nheavy_out)      // sorted descending: first position whose cost is not above the threshold
+        *nheavy_out = (int)(thrust::lower_bound(thrust::cuda::par.on(s), cost, cost + nchunk, QBX_HEAVY_TASK, thrust::greater<float>()) - cost);
+    QBX_CUDA(cudaStreamSynchronize(s));
+    cudaFree(cost);
+    return QBX_OK;
+}
 
 // ------------------------------------------------------------------ shell reconstruction
 static int comp_index(const int32_t *a) { return CIDX(a[1], a[2]); }
@@ -434,7 +477,7 @@ void Engine::release_store()
 {
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
-            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].gt_bra); cudaFree(tasks_[b][k].gt_grp); cudaFree(tasks_[b][k].gt_off);
+            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].gt_bra); cudaFree(tasks_[b][k].gt_grp); cudaFree(tasks_[b][k].gt_off); cudaFree(tasks_[b][k].order);
             tasks_[b][k] = TaskList();
             cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
         }
@@ -469,16 +512,18 @@ int Engine::eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, 
     a.counter = d_counters_ + counter_next_;
     counter_next_ = (counter_next_ + 1) % 1024;
     QBX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), s));
+    a.order = nullptr;
     return QBX_OK;
 }
 
-int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s)
+int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, const int *order)
 {
     const ClassOps *ops = qbx_class_ops(bc, kc);
     if (!ops) { qbx_set_error("internal: no kernel for this class"); return QBX_ERR_STATE; }
     ClassArgs a;
     int rc0 = eri_args(bc, kc, tasks, n, out, s, a);
     if (rc0) return rc0;
+    a.order = order;
     // Large classes (>= coop_min contracted accumulators per quartet) go to the warp-cooperative
     // kernel; QBX_COOP_MIN_ACC overrides the threshold (0 = every class, for tests).
     static const int coop_min = std::min(QBX_COOP_ACC, getenv("QBX_COOP_MIN_ACC") ? atoi(getenv("QBX_COOP_MIN_ACC")) : QBX_COOP_ACC);
@@ -531,7 +576,7 @@ int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskLi
     const int64_t total = rowoff.back();
     const int64_t nfull = total / QBX_TASK_CHUNK, rem = total % QBX_TASK_CHUNK;
     int64_t mine = 0;
-    for (int64_t c = rank; c < nfull; c += nranks) mine += QBX_TASK_CHUNK;
+    if (nfull > rank) mine = ((nfull - rank + nranks - 1) / nranks) * QBX_TASK_CHUNK;
     if (rem && nfull % nranks == rank) mine += rem;
     out.n = mine;
     out.nvalid = mine;
@@ -594,6 +639,10 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
             else
                 rc = build_tasks(bc, kc, tol, rank, nranks, tasks_[bc][kc], s);
             if (rc) return rc;
+            if (mode == 0 && tasks_[bc][kc].ngt == 0 && tasks_[bc][kc].n > 0 &&
+                (rc = qbx_chunk_order(tasks_[bc][kc].tasks, nullptr, nullptr, tasks_[bc][kc].n, pairs_[bc].prim_off,
+                                      pairs_[kc].prim_off, &tasks_[bc][kc].order, nullptr, s)))
+                return rc;
             const ClassOps *ops = qbx_class_ops(bc, kc);
             const TaskList &tl = tasks_[bc][kc];
             n_quartets_ += tl.nvalid;
@@ -671,7 +720,7 @@ int Engine::recompute(cudaStream_t s, double *stats, bool timed)
                 if ((rc = eri_args(bc, kc, tl.tasks, tl.n, vals_[bc][kc], cs, a))) return rc;
                 rc = qbx_group_eri(kClsLa[bc], groups_, a, tl, cs);
             } else {
-                rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], cs);
+                rc = run_eri(bc, kc, tl.tasks, tl.n, vals_[bc][kc], cs, tl.order);
             }
             if (rc) return rc;
             stats[0] += 1;

@@ -65,7 +65,13 @@ struct TaskList {
     // group tasks (eri_group.cu): task t covers the slots gt_off[t] .. gt_off[t] + nmem(gt_grp[t]) - 1
     int ngt = 0;
     int *gt_bra = nullptr, *gt_grp = nullptr, *gt_off = nullptr;
+    int *order = nullptr;                // 32-task chunks sorted by cost, heaviest first (LPT schedule for the work queue)
+    int nheavy = 0;                      // leading chunks of `order` whose tasks exceed QBX_HEAVY_TASK primitive quartets
 };
+// cost-sorted chunk order of a task list (tasks != null) or of a group-task list (tasks == null)
+int qbx_chunk_order(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poff_bra,
+                    const int *poff_ket, int **order_out, int *nheavy_out, cudaStream_t s);
+#define QBX_HEAVY_TASK 1024.0f
 
 // (ss) group pairs: ket-side general-contraction sharing, see eri_group.cu
 struct GroupSet {
@@ -105,7 +111,7 @@ private:
     int upload(bool pair_adjacent);
     int ensure_schwarz(cudaStream_t s);
     int build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s);
-    int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s);
+    int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, const int *order = nullptr);
     int eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a);
     bool grouped(int bc, int kc) const { return use_groups_ && kc == 0 && (bc == 0 || bc == 1); }   // (ss|ss), (ps|ss); (ds|ss) measured slower
     GroupSet groups_;

@@ -80,6 +80,7 @@ struct ClassArgs {
     const double *shell_scale; // [nshell][6] per-component weights
     BoysTable boys;
     unsigned int *counter;     // work queue head for this launch (zeroed by the host)
+    const int *order;          // 32-task chunks in processing order (heaviest first), or null = list order
 };
 
 __device__ __forceinline__ double4 ldg4(const double *p)
@@ -312,8 +313,9 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA + LB + LC + LD <= 2 ? 3 :
     for (;;) {
         unsigned int c = 0;
         if (lane == 0) c = atomicAdd(p.counter, 1u);
-        const int64_t chunk = __shfl_sync(0xffffffffu, c, 0);
-        if (chunk >= nchunk) break;
+        const int64_t k = __shfl_sync(0xffffffffu, c, 0);
+        if (k >= nchunk) break;
+        const int64_t chunk = p.order ? p.order[k] : k;
         const int64_t q = chunk * 32 + lane;
         if (q >= p.ntasks) continue;
         const int2 t = p.tasks[q];

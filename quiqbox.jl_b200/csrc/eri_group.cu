@@ -21,7 +21,7 @@
 
 #define QBX_GRP_MAXMEM 9
 #define QBX_GRP_NF (5 + QBX_GRP_MAXMEM)      // eta, Qx, Qy, Qz, Kgeom, cc[9]
-#define QBX_GRP_CHUNK 64                     // sharding granule in group tasks
+#define QBX_GRP_CHUNK 32                     // sharding granule in group tasks
 
 namespace {
 
@@ -120,6 +120,8 @@ struct GroupArgs {
     const double *shell_scale;
     BoysTable boys;
     unsigned int *counter;
+    const int *order;
+    int nheavy;                // leading chunks of `order` that are handed out one TASK per warp
 };
 
 template <int LA>
@@ -132,12 +134,22 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_
     __syncthreads();
     const int nchunk = (p.ntasks + 31) / 32;
     const int lane = threadIdx.x & 31;
-    for (;;) {                                               // per-warp work queue, see eri_class.cuh
+    // Work queue per warp (see eri_class.cuh).  The first 32 * nheavy positions hand out the tasks
+    // of the heaviest chunks ONE AT A TIME: a task with 81 x 81 primitive quartets keeps a lone
+    // thread busy for ~3 ms (its ~800-cycle dependent chain per primitive quartet is only hidden
+    // while other warps are resident), which sets the run time of the whole launch once the list
+    // is split over 8 GPUs.  Such a task is shared by the warp -- the lanes split the ket
+    // primitives, partial sums meet in a shuffle reduction.  All other chunks: one task per lane.
+    const int nq = 32 * p.nheavy + (nchunk - p.nheavy);
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    for (;;) {
         unsigned int cq = 0;
         if (lane == 0) cq = atomicAdd(p.counter, 1u);
-        const int chunk = (int)__shfl_sync(0xffffffffu, cq, 0);
-        if (chunk >= nchunk) break;
-        const int t = chunk * 32 + lane;
+        const int kq = (int)__shfl_sync(0xffffffffu, cq, 0);
+        if (kq >= nq) break;
+        const bool coop = kq < 32 * p.nheavy;
+        const int chunk = coop ? p.order[kq >> 5] : (p.order ? p.order[p.nheavy + (kq - 32 * p.nheavy)] : kq);
+        const int t = chunk * 32 + (coop ? (kq & 31) : lane);
         if (t >= p.ntasks) continue;
         const int ib = p.gt_bra[t], g = p.gt_grp[t], off = p.gt_off[t];
         const double *gb = p.bra.geom + 8 * (int64_t)ib;
@@ -145,18 +157,17 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_
         const int pb0 = p.bra.prim_off[ib], pb1 = p.bra.prim_off[ib + 1];
         const int nk = p.grp_prim_off[g + 1] - p.grp_prim_off[g];
         const int2 si = p.grp_soa_idx[g];
+        const int nmem = p.grp_nmem[g];
         double acc[QBX_GRP_MAXMEM][NA];
 #pragma unroll
         for (int m = 0; m < QBX_GRP_MAXMEM; ++m)
 #pragma unroll
             for (int c = 0; c < NA; ++c) acc[m][c] = 0.0;
-        const double zero3[3] = {0.0, 0.0, 0.0};
-        const int nmem = p.grp_nmem[g];
         // ket primitive outermost: its record and the members' coefficient products are loaded once,
-        // the (warp-uniform) bra primitives run inside, and the coefficient contraction happens once
-        // per ket primitive instead of once per primitive quartet
-        const double *kp = p.grp_soa + si.x;
-        for (int pk = 0; pk < nk; ++pk, kp += QBX_GRP_NF * si.y) {
+        // the bra primitives run inside, and the coefficient contraction happens once per ket
+        // primitive instead of once per primitive quartet
+        for (int pk = coop ? lane : 0; pk < nk; pk += coop ? 32 : 1) {
+            const double *kp = p.grp_soa + si.x + (int64_t)pk * QBX_GRP_NF * si.y;
             const double eta = __ldg(kp);
             const double Q[3] = {__ldg(kp + si.y), __ldg(kp + 2 * si.y), __ldg(kp + 3 * si.y)};
             const double Kg = __ldg(kp + 4 * si.y);
@@ -179,6 +190,15 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_
                 }
             }
         }
+        if (coop) {
+#pragma unroll
+            for (int m = 0; m < QBX_GRP_MAXMEM; ++m)
+#pragma unroll
+                for (int c = 0; c < NA; ++c)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[m][c] += __shfl_xor_sync(0xffffffffu, acc[m][c], o);
+            if (lane != 0) continue;
+        }
         const int2 sb = p.bra.shells[ib];
         const double *sA = p.shell_scale + 6 * sb.x;
         const double sB = p.shell_scale[6 * sb.y];
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_
 }
 
 template <int LA>
-int launch_group(const GroupArgs &a, cudaStream_t s)
+int launch_group(GroupArgs a, cudaStream_t s)
 {
     static int max_blocks = 0;
     if (max_blocks == 0) {
@@ -209,6 +229,10 @@ int launch_group(const GroupArgs &a, cudaStream_t s)
         max_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
     const int need = (a.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    // task-granular hand-out of the heavy chunks only when the launch is short (few chunks per
+    // resident warp), i.e. when the tail decides; on a long list the one-task-per-lane mode is
+    // ~8 % faster and the tail is filled by the light chunks anyway
+    if ((a.ntasks + 31) / 32 >= 8 * max_blocks * (QBX_ERI_THREADS / 32)) a.nheavy = 0;
     eri_group_kernel<LA><<<need < max_blocks ? need : max_blocks, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
@@ -396,6 +420,8 @@ int qbx_group_tasks(const GroupSet &G, const DevPairSet &B, const DevPairSet &K,
         cudaFree(d_st);
         tl.nvalid = (int64_t)st[0];
         tl.nprimq = st[1];
+        int rc = qbx_chunk_order(nullptr, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, &tl.order, &tl.nheavy, s);
+        if (rc) return rc;
     }
     cudaFree(d_c0); cudaFree(d_c1); cudaFree(d_c2); cudaFree(d_o0); cudaFree(d_o1); cudaFree(d_o2);
     return QBX_OK;
@@ -408,7 +434,7 @@ int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList 
     g.bra = a.bra; g.ket = a.ket; g.tasks = tl.tasks; g.nslots = tl.n;
     g.gt_bra = tl.gt_bra; g.gt_grp = tl.gt_grp; g.gt_off = tl.gt_off; g.ntasks = tl.ngt;
     g.grp_nmem = G.nmem; g.grp_prim_off = G.prim_off; g.grp_soa = G.soa; g.grp_soa_idx = G.soa_idx;
-    g.out = a.out; g.shell_scale = a.shell_scale; g.boys = a.boys; g.counter = a.counter;
+    g.out = a.out; g.shell_scale = a.shell_scale; g.boys = a.boys; g.counter = a.counter; g.order = tl.order; g.nheavy = tl.order ? tl.nheavy : 0;
     switch (la) {
     case 0: return launch_group<0>(g, s);
     case 1: return launch_group<1>(g, s);

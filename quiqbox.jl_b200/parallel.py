@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 
-def shard_chunks(total_tasks: int, nranks: int, chunk: int = 256):
+def shard_chunks(total_tasks: int, nranks: int, chunk: int = 32):
     """Host mirror of the library's sharding rule (engine.cu: build_tasks): tasks are cut in
     chunks of ``chunk``; rank r owns chunks r, r + nranks, ...  Returns the task count per rank."""
     nfull, rem = divmod(total_tasks, chunk)

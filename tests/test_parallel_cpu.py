@@ -15,7 +15,7 @@ def test_shard_chunks_partition():
         for n in (1, 2, 3, 8):
             parts = shard_chunks(total, n)
             assert sum(parts) == total and len(parts) == n
-            assert max(parts) - min(parts) <= 256            # balanced to one chunk
+            assert max(parts) - min(parts) <= 32             # balanced to one chunk
 
 
 def _worker(rank, world, port, q):
