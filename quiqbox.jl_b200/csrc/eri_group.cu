@@ -125,7 +125,7 @@ struct GroupArgs {
 };
 
 template <int LA>
-__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA <= 1 ? 3 : 1)) eri_group_kernel(GroupArgs p)
+__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA == 0 ? 3 : (LA == 1 ? 2 : 1))) eri_group_kernel(GroupArgs p)
 {
     using EC = EriClass<LA, 0, 0, 0>;
     constexpr int NA = NC(LA);
