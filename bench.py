@@ -75,7 +75,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,8 +89,9 @@ class ClockSampler:
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+            time.sleep(0.25)
+            self.proc.kill()                 # a lingering nvidia-smi poller slows every CUDA API call
+            self.proc.wait()
             self.t.join(timeout=2)
 
     def summary(self):
