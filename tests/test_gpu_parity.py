@@ -342,3 +342,38 @@ def test_sad_guess_and_default_config():
         for hf, key in ((qb.RCHartreeFock(), "rhfs"), (qb.UOHartreeFock(), "uhfs")):
             r = qb.runHartreeFock((nuc, xyz), mol_basis(nuc, xyz, "3-21G"), qb.HFconfig(HF=hf, initial=":SAD", maxStep=300))
             assert sum(r.energy) == pytest.approx(g[key][k], abs=7.5e-7), (k, key)
+
+
+def test_general_contraction_sharing_on_off():
+    """QBX_GC=0 disables the ket-side primitive-group sharing of the (ss|ss)/(ps|ss) classes (eri_group.cu);
+    the Fock build must not change beyond rounding, and both must match the oracle contraction."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path[:0] = [%r, %r]
+import quiqbox_b200 as qb
+from molecules import water_cluster
+nuc, xyz = water_cluster(3)
+bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+n = len(bs)
+rng = np.random.RandomState(5); D = rng.uniform(-1, 1, (n, n)); D = (D + D.T) / 2
+G = qb.DeviceERI(bs, mode="stored", screen_tol=1e-13).getGcore(2 * D, [D])[0]
+np.save(sys.argv[1], G)
+''' % (os.path.dirname(HERE), HERE)
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        for gc in ("0", "1"):
+            f = os.path.join(td, f"g{gc}.npy")
+            r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, QBX_GC=gc), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            out[gc] = np.load(f)
+    assert np.max(np.abs(out["0"] - out["1"])) < 1e-10
+    nuc, xyz = water_cluster(3)
+    bs = mol_basis(nuc, xyz, "cc-pVDZ")
+    T = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs)).eri_tensor()
+    n = len(bs)
+    rng = np.random.RandomState(5); D = rng.uniform(-1, 1, (n, n)); D = (D + D.T) / 2
+    assert np.max(np.abs(out["1"] - oracle.getGcore(T, 2 * D, D))) < 1e-9
