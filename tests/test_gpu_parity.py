@@ -377,3 +377,31 @@ np.save(sys.argv[1], G)
     n = len(bs)
     rng = np.random.RandomState(5); D = rng.uniform(-1, 1, (n, n)); D = (D + D.T) / 2
     assert np.max(np.abs(out["1"] - oracle.getGcore(T, 2 * D, D))) < 1e-9
+
+
+def test_irregular_basis_falls_back_to_generic_kernels():
+    """Ingestion: functions that do not factor into s/p/d shells -- an f function and a
+    contracted function whose primitives sit on two centres (README.md:21-22 of the reference: "mixed-
+    contracted" orbitals) -- switch the whole basis to the generic per-function kernels and the dense mode."""
+    nuc, xyz = h2o()
+    bs = mol_basis(nuc, xyz, "6-31G")
+    bs.append(qb.genGaussTypeOrb(xyz[0], 1.1, (1, 1, 1)))                          # f_xyz primitive on O
+    db = qb.DeviceBasis(bs)
+    assert db.info()["class_path"] == 0
+    ob = oracle.OracleBasis(db.data)
+    T = qb.elecRepulsions(db)
+    Tref = ob.eri_tensor()
+    assert np.max(np.abs(T - Tref)) < 1e-12
+    n = db.nbf
+    DJ, DK = _rand_sym(n, 61), _rand_sym(n, 62)
+    G = qb.DeviceERI(db, mode="stored").getGcore(DJ, [DK])[0]                       # silently dense: no shells
+    assert np.max(np.abs(G - oracle.getGcore(Tref, DJ, DK))) < 1e-10
+    # two-centre contraction: flat table built by hand (one function = primitives on O and on H)
+    m = qb.MultiOrbitalData.from_orbitals(mol_basis(nuc, xyz, "STO-3G"))
+    off = list(m.bf_off) + [m.bf_off[-1] + 2]
+    mixed = qb.MultiOrbitalData(m.cen, m.xpn, m.ang, np.array(off, dtype=np.int64),
+                                np.concatenate([m.bf_prim, [0, m.nprim - 1]]).astype(np.int64),
+                                np.concatenate([m.bf_w, [0.7, -0.4]]))
+    dm = qb.DeviceBasis(mixed)
+    assert dm.info()["class_path"] == 0
+    assert np.max(np.abs(qb.elecRepulsions(dm) - oracle.OracleBasis(mixed).eri_tensor())) < 1e-12
