@@ -358,7 +358,7 @@ nuc, xyz = water_cluster(3)
 bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
 n = len(bs)
 rng = np.random.RandomState(5); D = rng.uniform(-1, 1, (n, n)); D = (D + D.T) / 2
-G = qb.DeviceERI(bs, mode="stored", screen_tol=1e-13).getGcore(2 * D, [D])[0]
+G = qb.DeviceERI(bs, mode="stored", screen_tol=0.0).getGcore(2 * D, [D])[0]
 np.save(sys.argv[1], G)
 ''' % (os.path.dirname(HERE), HERE)
     import tempfile
