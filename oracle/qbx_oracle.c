@@ -472,6 +472,34 @@ double orc_eri_quartet(const orc_basis *b, int64_t i, int64_t j, int64_t k, int6
     return res;
 }
 
+/* The same integral in the "l-canonical" orientation: by the 8-fold permutational symmetry
+ * (ij|kl) = (ji|kl) = (kl|ij) = ..., so the reference's routine may be called with the pair of
+ * higher angular momentum as electron 1 and, inside each pair, the higher-l function first (the
+ * centre the vertical recurrence is built on).  Mathematically identical; numerically it is NOT:
+ * the reference evaluates in index order (i <= j, k <= l, ij <= kl, Framework.jl:651-653) and
+ * builds all angular momentum on function i's centre before transferring it to electron 2
+ * (GaussianOrbitals.jl:637-660).  For e.g. (s_H s_O | d_O d_O) with the 11720-exponent O
+ * primitive that is a 5-bohr PA raised to the 4th power followed by four transfer levels with
+ * zeta/eta = 4900, and the result loses 11 digits (tests/test_oracle_golden.py::
+ * test_reference_orientation_instability).  The shell-class CUDA kernels always work in the
+ * canonical orientation, so at scale they are compared with this entry point. */
+static int orc_fn_l(const orc_basis *b, int64_t f)
+{
+    const int64_t p = b->bf_prim[b->bf_off[f]];
+    return b->ang[3 * p] + b->ang[3 * p + 1] + b->ang[3 * p + 2];
+}
+
+double orc_eri_quartet_canonical(const orc_basis *b, int64_t i, int64_t j, int64_t k, int64_t l)
+{
+    int li = orc_fn_l(b, i), lj = orc_fn_l(b, j), lk = orc_fn_l(b, k), ll = orc_fn_l(b, l);
+    int64_t t;
+    int tl;
+    if (lj > li) { t = i; i = j; j = t; tl = li; li = lj; lj = tl; }
+    if (ll > lk) { t = k; k = l; l = t; tl = lk; lk = ll; ll = tl; }
+    if (lk + ll > li + lj || (lk + ll == li + lj && lk > li)) { t = i; i = k; k = t; t = j; j = l; l = t; }
+    return orc_eri_quartet(b, i, j, k, l);
+}
+
 static inline void orc_tri2(int64_t n, int64_t *i, int64_t *j)
 {   /* convertIndex1DtoTri2D, Iteration.jl:7-12, 0-based here: n -> (i <= j) */
     int64_t jj = (int64_t)((sqrt(8.0 * (double)(n + 1) - 6.9) - 1.0) / 2.0);
@@ -483,8 +511,9 @@ static inline void orc_tri2(int64_t n, int64_t *i, int64_t *j)
 /* getOrbVectorIntegralCore! two-body, Framework.jl:640-665: column-major N^4 tensor,
  * tensor[i,j,k,l] = (ij|kl), filled from the M(M+1)/2 unique entries and their images.
  * `parallel` = 0 keeps the reference's serial loop; 1 spreads the unique-entry loop over
- * OpenMP threads (the values are identical; only used to make fixtures affordable). */
-void orc_eri_tensor(const orc_basis *b, double *T, int parallel)
+ * OpenMP threads (the values are identical; only used to make fixtures affordable).
+ * `canonical` = 1 evaluates every entry through orc_eri_quartet_canonical. */
+void orc_eri_tensor(const orc_basis *b, double *T, int parallel, int canonical)
 {
     int64_t N = b->nbf, M = N * (N + 1) / 2, U = M * (M + 1) / 2;
 #pragma omp parallel for schedule(dynamic, 64) if (parallel)
@@ -493,7 +522,7 @@ void orc_eri_tensor(const orc_basis *b, double *T, int parallel)
         orc_tri2(n, &p, &q);
         orc_tri2(p, &i, &j);
         orc_tri2(q, &k, &l);
-        double v = orc_eri_quartet(b, i, j, k, l);
+        double v = canonical ? orc_eri_quartet_canonical(b, i, j, k, l) : orc_eri_quartet(b, i, j, k, l);
 #define AT(a, bb, c, d) T[(a) + N * ((bb) + N * ((c) + N * (d)))]
         AT(i, j, k, l) = v; AT(j, i, k, l) = v; AT(i, j, l, k) = v; AT(j, i, l, k) = v;
         AT(k, l, i, j) = v; AT(k, l, j, i) = v; AT(l, k, i, j) = v; AT(l, k, j, i) = v;
@@ -501,11 +530,12 @@ void orc_eri_tensor(const orc_basis *b, double *T, int parallel)
     }
 }
 
-void orc_eri_list(const orc_basis *b, int64_t n, const int64_t *ijkl, double *out, int parallel)
+void orc_eri_list(const orc_basis *b, int64_t n, const int64_t *ijkl, double *out, int parallel, int canonical)
 {
 #pragma omp parallel for schedule(dynamic, 16) if (parallel)
     for (int64_t t = 0; t < n; ++t)
-        out[t] = orc_eri_quartet(b, ijkl[4 * t], ijkl[4 * t + 1], ijkl[4 * t + 2], ijkl[4 * t + 3]);
+        out[t] = canonical ? orc_eri_quartet_canonical(b, ijkl[4 * t], ijkl[4 * t + 1], ijkl[4 * t + 2], ijkl[4 * t + 3])
+                           : orc_eri_quartet(b, ijkl[4 * t], ijkl[4 * t + 1], ijkl[4 * t + 2], ijkl[4 * t + 3]);
 }
 
 /* one-body matrices: kind 0 overlap, 1 kinetic, 2 nuclear attraction (sum_C -Z_C/|r-C|:

@@ -109,8 +109,27 @@ __device__ double prim_eri_generic(const Prim &A, const Prim &B, const Prim &C, 
     return pref * g[0];
 }
 
+__device__ inline int fn_l(const DevFlat &f, int64_t fn)
+{
+    const int64_t p = f.bf_prim[f.bf_off[fn]];
+    return f.ang[3 * p] + f.ang[3 * p + 1] + f.ang[3 * p + 2];
+}
+
+// The quartet is first brought into the l-canonical orientation (higher-l pair = electron 1,
+// higher-l function first in each pair): (ij|kl) is invariant, but the recurrences build all
+// angular momentum on the first function's centre and then transfer it to electron 2, which loses
+// up to 11 digits when that centre is far from a tight partner and the angular momentum sits on
+// the other electron (the reference's index-order evaluation has exactly this problem; DESIGN.md
+// section 2).
 __device__ double contracted_eri_generic(const DevFlat &f, int64_t i, int64_t j, int64_t k, int64_t l)
 {
+    {
+        int li = fn_l(f, i), lj = fn_l(f, j), lk = fn_l(f, k), ll = fn_l(f, l);
+        int64_t t; int tl;
+        if (lj > li) { t = i; i = j; j = t; tl = li; li = lj; lj = tl; }
+        if (ll > lk) { t = k; k = l; l = t; tl = lk; lk = ll; ll = tl; }
+        if (lk + ll > li + lj || (lk + ll == li + lj && lk > li)) { t = i; i = k; k = t; t = j; j = l; l = t; }
+    }
     double res = 0.0;
     for (int64_t s = f.bf_off[l]; s < f.bf_off[l + 1]; ++s) {
         const Prim D = load_prim(f, f.bf_prim[s]);

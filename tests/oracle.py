@@ -93,17 +93,21 @@ class OracleBasis:
     def eri(self, i, j, k, l):
         return lib().orc_eri_quartet(C.byref(self.s), i, j, k, l)
 
-    def eri_list(self, ijkl, parallel=True):
+    def eri_list(self, ijkl, parallel=True, canonical=False):
+        """canonical=True: same integrals, evaluated in the l-canonical orientation (see
+        orc_eri_quartet_canonical: the reference's index-order evaluation is numerically unstable for
+        a few (s s|d d)-type entries)."""
         ijkl = np.ascontiguousarray(ijkl, dtype=np.int64).reshape(-1, 4)
         out = np.zeros(len(ijkl))
-        lib().orc_eri_list(C.byref(self.s), C.c_int64(len(ijkl)), _p(ijkl), _p(out), C.c_int(int(parallel)))
+        lib().orc_eri_list(C.byref(self.s), C.c_int64(len(ijkl)), _p(ijkl), _p(out), C.c_int(int(parallel)),
+                           C.c_int(int(canonical)))
         return out
 
-    def eri_tensor(self, parallel=True):
+    def eri_tensor(self, parallel=True, canonical=False):
         """N^4 tensor, T[i,j,k,l] = (ij|kl) (numpy index order = the reference's)."""
         n = self.nbf
         out = np.zeros(n ** 4)
-        lib().orc_eri_tensor(C.byref(self.s), _p(out), C.c_int(int(parallel)))
+        lib().orc_eri_tensor(C.byref(self.s), _p(out), C.c_int(int(parallel)), C.c_int(int(canonical)))
         return out.reshape((n, n, n, n), order="F")
 
     def one_body(self, kind, Z=None, R=None):

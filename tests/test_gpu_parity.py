@@ -177,7 +177,8 @@ def _sampled_eri_check(bs, nsample, seed):
     ob = oracle.OracleBasis(db.data)
     rng = np.random.RandomState(seed)
     idx = rng.randint(0, db.nbf, size=(nsample, 4))
-    return db, idx, ob.eri_list(idx)
+    # l-canonical orientation: see test_oracle_golden.py::test_reference_orientation_instability
+    return db, idx, ob.eri_list(idx, canonical=True)
 
 
 def test_benzene_ccpvdz_sampled_and_fock_consistency():
@@ -373,10 +374,12 @@ np.save(sys.argv[1], G)
     assert np.max(np.abs(out["0"] - out["1"])) < 1e-10
     nuc, xyz = water_cluster(3)
     bs = mol_basis(nuc, xyz, "cc-pVDZ")
-    T = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs)).eri_tensor()
+    T = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs)).eri_tensor(canonical=True)
     n = len(bs)
     rng = np.random.RandomState(5); D = rng.uniform(-1, 1, (n, n)); D = (D + D.T) / 2
     assert np.max(np.abs(out["1"] - oracle.getGcore(T, 2 * D, D))) < 1e-9
+    # ... and the class-kernel tensor itself, entry by entry (31.6 M entries, 3 molecules)
+    assert np.max(np.abs(qb.elecRepulsions(bs) - T)) < 1e-12
 
 
 def test_irregular_basis_falls_back_to_generic_kernels():

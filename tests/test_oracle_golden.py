@@ -175,3 +175,28 @@ def test_h2o2_631g_default_config_sad_guess():
     for cfg in (HFconfig(), HFconfig(initial=":SAD", strategy=SCFconfig(threshold=5e-10, secondaryConvRatio=(5, 5)))):
         out = runHartreeFockCore(S, H, g, (ne // 2,), cfg, sad)
         assert out[5] and out[4] == pytest.approx(-187.42063898359095, abs=2.5e-9)
+
+
+def test_reference_orientation_instability():
+    """A finding, pinned: the reference evaluates (ij|kl) in index order and builds all angular momentum
+    on function i's centre before transferring it to electron 2.  For (s_H s_O|d_O d_O)-type entries with
+    the 11720-exponent O primitive the result loses ~11 digits: the faithful oracle (and hence, by
+    construction, Quiqbox's own tensor) is off by up to 2.8e-5 on 208 of the 6.25 M entries of
+    (H2O)2/cc-pVDZ, while the same routine called in any l-canonical orientation agrees with itself to
+    1e-15.  The CUDA class kernels work in the canonical orientation; tests at scale therefore use
+    OracleBasis(..., canonical=True)."""
+    from molecules import water_cluster
+    nuc, xyz = water_cluster(2)
+    bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+    ob = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs))
+    T, Tc = ob.eri_tensor(), ob.eri_tensor(canonical=True)
+    d = np.abs(T - Tc)
+    assert 1e-6 < d.max() < 1e-4 and 50 < int((d > 1e-10).sum()) < 1000
+    i, j, k, l = (int(x) for x in np.unravel_index(np.argmax(d), d.shape))
+    ls = [sum(bs[f].ang) for f in (i, j, k, l)]
+    assert sorted(ls) == [0, 0, 2, 2]                                  # two s functions, two d functions
+    stable = [ob.eri(*p) for p in ((k, l, i, j), (k, l, j, i), (l, k, i, j), (l, k, j, i))] if ls[0] == 0 else \
+             [ob.eri(*p) for p in ((i, j, k, l), (j, i, k, l), (i, j, l, k), (j, i, l, k))]
+    assert max(stable) - min(stable) < 1e-15 and abs(Tc[i, j, k, l] - stable[0]) < 1e-15
+    # the canonical tensor keeps the exact 8-fold symmetry and leaves the single-molecule goldens untouched
+    assert np.array_equal(Tc, Tc.transpose(2, 3, 0, 1)) and np.array_equal(Tc, Tc.transpose(1, 0, 2, 3))
