@@ -137,6 +137,15 @@ int qbx_class_stats(qbx_basis *b, double *out);
  * the roofline denominator of the ERI kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int qbx_fp64_peak(double *tflops);
 
+/* Device allocations of the library (basis tables, task lists, the packed ERI store) come from
+ * a size-keyed pool, so that the create -> store -> destroy cycle of a geometry scan or an
+ * optimisation (reference: src/HartreeFock.jl:583-606 runs once per geometry) does not pay
+ * cudaMalloc/cudaFree of a multi-GB store every time.  Environment QBX_POOL_GB = cap on idle
+ * cached bytes (default 64, 0 = no pooling).  qbx_pool_trim returns the idle blocks to the
+ * driver; counts (nullable) receives [0] reuses, [1] driver allocations, [2] idle bytes before
+ * the trim. */
+int qbx_pool_trim(int64_t *counts);
+
 /* counters since the last reset: [0] kernels launched, [1] device seconds in ERI kernels,
  * [2] device seconds in digestion kernels, [3] primitive quartets evaluated,
  * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */

@@ -41,7 +41,7 @@ def build(jobs=None, force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     work, objs = [], []
-    for name in ("api", "generic", "engine", "eri_coop", "eri_group"):
+    for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool"):
         src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):

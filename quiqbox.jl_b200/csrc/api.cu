@@ -47,8 +47,8 @@ static int build_boys_table()
         for (int m = 0; m < QBX_BOYS_NCOL; ++m) f[(size_t)i * QBX_BOYS_NCOL + m] = (double)row[m];
         e[i] = (double)expl(-T);
     }
-    QBX_CUDA(cudaMalloc(&g_boys_f, f.size() * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&g_boys_e, e.size() * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&g_boys_f, f.size() * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&g_boys_e, e.size() * sizeof(double)));
     QBX_CUDA(cudaMemcpy(g_boys_f, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
     QBX_CUDA(cudaMemcpy(g_boys_e, e.data(), e.size() * sizeof(double), cudaMemcpyHostToDevice));
     return QBX_OK;
@@ -73,13 +73,21 @@ extern "C" int qbx_init(int device, int *n_dev_out)
     return QBX_OK;
 }
 
+extern "C" int qbx_pool_trim(int64_t *counts)
+{
+    if (counts) qbx_pool_counts(counts, counts + 1, counts + 2);
+    qbx_pool_release();
+    return QBX_OK;
+}
+
 extern "C" int qbx_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_device < 0) return QBX_OK;
     cudaSetDevice(g_device);
-    cudaFree(g_boys_f); cudaFree(g_boys_e);
+    qbx_pool_free(g_boys_f); qbx_pool_free(g_boys_e);
     g_boys_f = g_boys_e = nullptr;
+    qbx_pool_release();
     cudaStreamDestroy(g_own_stream);
     g_stream = g_own_stream = nullptr;
     g_device = -1;
@@ -116,7 +124,7 @@ struct qbx_basis {
 template <class T>
 static int to_device(T **dst, const std::vector<T> &src)
 {
-    QBX_CUDA(cudaMalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+    QBX_CUDA(qbx_dmalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
     if (!src.empty()) QBX_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
     return QBX_OK;
 }
@@ -163,7 +171,7 @@ extern "C" int qbx_basis_create(int64_t nprim, const double *cen, const double *
 
 static void free_store(qbx_basis *b)
 {
-    cudaFree(b->d_dense); b->d_dense = nullptr;
+    qbx_pool_free(b->d_dense); b->d_dense = nullptr;
     if (b->eng) b->eng->release_store();
     b->mode = -1;
 }
@@ -173,9 +181,9 @@ extern "C" int qbx_basis_destroy(qbx_basis *b)
     if (!b) return QBX_OK;
     if (g_device >= 0) cudaSetDevice(g_device);
     free_store(b);
-    cudaFree(b->flat.cen); cudaFree(b->flat.xpn); cudaFree(b->flat.ang);
-    cudaFree(b->flat.bf_off); cudaFree(b->flat.bf_prim); cudaFree(b->flat.bf_w);
-    cudaFree(b->d_DJ); cudaFree(b->d_DK); cudaFree(b->d_G);
+    qbx_pool_free(b->flat.cen); qbx_pool_free(b->flat.xpn); qbx_pool_free(b->flat.ang);
+    qbx_pool_free(b->flat.bf_off); qbx_pool_free(b->flat.bf_prim); qbx_pool_free(b->flat.bf_w);
+    qbx_pool_free(b->d_DJ); qbx_pool_free(b->d_DK); qbx_pool_free(b->d_G);
     delete b;
     return QBX_OK;
 }
@@ -199,8 +207,8 @@ extern "C" int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, do
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     int64_t *d_idx = nullptr; double *d_out = nullptr;
-    QBX_CUDA(cudaMalloc(&d_idx, 4 * n * sizeof(int64_t)));
-    QBX_CUDA(cudaMalloc(&d_out, n * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&d_idx, 4 * n * sizeof(int64_t)));
+    QBX_CUDA(qbx_dmalloc(&d_out, n * sizeof(double)));
     QBX_CUDA(cudaMemcpyAsync(d_idx, ijkl, 4 * n * sizeof(int64_t), cudaMemcpyHostToDevice, g_stream));
     rc = qbx_launch_generic_quartets(b->flat, n, d_idx, d_out, g_stream);
     if (!rc) {
@@ -208,7 +216,7 @@ extern "C" int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, do
         QBX_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(d_idx); cudaFree(d_out);
+    qbx_pool_free(d_idx); qbx_pool_free(d_out);
     if (!rc)
         for (int64_t t = 0; t < n; ++t)
             if (out[t] != out[t]) { qbx_set_error("qbx_eri_quartets: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
@@ -224,14 +232,14 @@ extern "C" int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes)
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     double *d_t = nullptr;
-    QBX_CUDA(cudaMalloc(&d_t, need));
+    QBX_CUDA(qbx_dmalloc(&d_t, need));
     if (b->eng) rc = b->eng->fill_tensor(d_t, g_stream, b->stats);
     else { rc = qbx_launch_generic_tensor(b->flat, d_t, g_stream); b->stats[0] += 1; }
     if (!rc) {
         QBX_CUDA(cudaMemcpyAsync(out, d_t, need, cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(d_t);
+    qbx_pool_free(d_t);
     return rc;
 }
 
@@ -248,7 +256,7 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
     if (mode == 2 || !b->eng) {
         if (nranks != 1) { qbx_set_error("qbx_eri_store: the dense mode does not shard"); return QBX_ERR_ARG; }
         const int64_t N = b->nbf, need = N * N * N * N * (int64_t)sizeof(double);
-        QBX_CUDA(cudaMalloc(&b->d_dense, need));
+        QBX_CUDA(qbx_dmalloc(&b->d_dense, need));
         if (b->eng) rc = b->eng->fill_tensor(b->d_dense, g_stream, b->stats);
         else { rc = qbx_launch_generic_tensor(b->flat, b->d_dense, g_stream); b->stats[0] += 1; }
         if (rc) return rc;
@@ -320,7 +328,7 @@ extern "C" int qbx_fp64_peak(double *tflops)
     QBX_CUDA(cudaGetDeviceProperties(&prop, g_device));
     const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
     double *d = nullptr;
-    QBX_CUDA(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&d, (size_t)blocks * 256 * sizeof(double)));
     cudaEvent_t e0, e1;
     QBX_CUDA(cudaEventCreate(&e0));
     QBX_CUDA(cudaEventCreate(&e1));
@@ -335,7 +343,7 @@ extern "C" int qbx_fp64_peak(double *tflops)
         const double tf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) * 1e-12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); qbx_pool_free(d);
     *tflops = best;
     return QBX_OK;
 }
@@ -367,10 +375,10 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
     if (b->staged_nmat < nmat) {
-        cudaFree(b->d_DJ); cudaFree(b->d_DK); cudaFree(b->d_G);
-        QBX_CUDA(cudaMalloc(&b->d_DJ, n2));
-        QBX_CUDA(cudaMalloc(&b->d_DK, n2 * 2));
-        QBX_CUDA(cudaMalloc(&b->d_G, n2 * 2));
+        qbx_pool_free(b->d_DJ); qbx_pool_free(b->d_DK); qbx_pool_free(b->d_G);
+        QBX_CUDA(qbx_dmalloc(&b->d_DJ, n2));
+        QBX_CUDA(qbx_dmalloc(&b->d_DK, n2 * 2));
+        QBX_CUDA(qbx_dmalloc(&b->d_G, n2 * 2));
         b->staged_nmat = 2;
     }
     QBX_CUDA(cudaMemcpyAsync(b->d_DJ, DJ, n2, cudaMemcpyHostToDevice, g_stream));
@@ -393,10 +401,10 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
     double *dZ = nullptr, *dR = nullptr, *dO = nullptr;
-    QBX_CUDA(cudaMalloc(&dO, n2));
+    QBX_CUDA(qbx_dmalloc(&dO, n2));
     if (kind == 2 && nnuc > 0) {
-        QBX_CUDA(cudaMalloc(&dZ, nnuc * sizeof(double)));
-        QBX_CUDA(cudaMalloc(&dR, 3 * nnuc * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&dZ, nnuc * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&dR, 3 * nnuc * sizeof(double)));
         QBX_CUDA(cudaMemcpyAsync(dZ, Z, nnuc * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         QBX_CUDA(cudaMemcpyAsync(dR, R, 3 * nnuc * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     }
@@ -406,7 +414,7 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
         QBX_CUDA(cudaMemcpyAsync(out, dO, n2, cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(dZ); cudaFree(dR); cudaFree(dO);
+    qbx_pool_free(dZ); qbx_pool_free(dR); qbx_pool_free(dO);
     return rc;
 }
 
@@ -422,15 +430,15 @@ extern "C" int qbx_boys(int64_t n, const double *T, int mmax, int table, double 
     int rc = ensure_init();
     if (rc) return rc;
     double *dT = nullptr, *dO = nullptr;
-    QBX_CUDA(cudaMalloc(&dT, n * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&dO, n * (mmax + 1) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&dT, n * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&dO, n * (mmax + 1) * sizeof(double)));
     QBX_CUDA(cudaMemcpyAsync(dT, T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     rc = qbx_launch_boys(n, dT, mmax, table, dO, g_stream);
     if (!rc) {
         QBX_CUDA(cudaMemcpyAsync(out, dO, n * (mmax + 1) * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(dT); cudaFree(dO);
+    qbx_pool_free(dT); qbx_pool_free(dO);
     return rc;
 }
 

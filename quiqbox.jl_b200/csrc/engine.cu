@@ -1,4 +1,6 @@
 // Host orchestration of the shell-quartet path (see engine.h).
+#include <chrono>
+#include <cstdio>
 #include "engine.h"
 #include "digest.cuh"
 
@@ -110,15 +112,49 @@ __global__ void k_schwarz(const double *vals, int n, int nab, double *Q)
     Q[i] = sqrt(m);
 }
 
+// one warp per bra row
 __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol, int *cnt)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (i >= nb) return;
     const int jmax = same ? i + 1 : nk;
     const double qi = Qb[i];
     int c = 0;
-    for (int j = 0; j < jmax; ++j) c += (qi * Qk[j] >= tol);
-    cnt[i] = c;
+    for (int j = lane; j < jmax; j += 32) c += (qi * Qk[j] >= tol);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[i] = c;
+}
+
+// off[i] = cnt[0] + .. + cnt[i-1], off[n] = *total = the sum: one block walks over the array
+__global__ void __launch_bounds__(1024) k_scan_counts(const int *cnt, int n, int64_t *off, int64_t *total)
+{
+    __shared__ int64_t wsum[32];
+    __shared__ int64_t tile_sum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int64_t v = i < n ? cnt[i] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            const int64_t t = wsum[lane];
+            int64_t z = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+            wsum[lane] = z - t;
+            if (lane == 31) tile_sum = z;
+        }
+        __syncthreads();
+        if (i < n) off[i] = carry + wsum[w] + x - v;
+        carry += tile_sum;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { off[n] = carry; if (total) *total = carry; }
 }
 
 // Sharding granule: rank r owns chunks r, r + nranks, ...  One chunk = one warp's worth of tasks.
@@ -189,7 +225,7 @@ __global__ void k_permute_in(int64_t Next, int64_t Nint, const int *ext_of_int, 
 
 // cost of every 32-task chunk = primitive quartets behind its tasks
 __global__ void k_chunk_cost(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poffb,
-                             const int *poffk, float *cost)
+                             const int *poffk, float *cost, int *nheavy)
 {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;       // blockDim multiple of 32
     float c = 0.f;
@@ -200,7 +236,10 @@ __global__ void k_chunk_cost(const int2 *tasks, const int *gt_bra, const int *gt
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));   // a warp runs at its slowest lane
-    if ((threadIdx.x & 31) == 0 && q < n + 31) cost[q / 32] = c;
+    if ((threadIdx.x & 31) == 0 && q < n + 31) {
+        cost[q / 32] = c;
+        if (nheavy && c > QBX_HEAVY_TASK) atomicAdd(nheavy, 1);
+    }
 }
 
 __global__ void k_sum(const double *v, int64_t n, double *sum)
@@ -219,25 +258,50 @@ __global__ void k_sum(const double *v, int64_t n, double *sum)
 
 }  // namespace
 
+void qbx_scan_counts(const int *cnt, int n, int64_t *off, int64_t *d_total, cudaStream_t s)
+{
+    k_scan_counts<<<1, 1024, 0, s>>>(cnt, n, off, d_total);
+}
+
+namespace {
+// temporary storage of the thrust algorithms comes from the library's pool (no cudaMalloc/cudaFree)
+struct PoolAllocator {
+    typedef char value_type;
+    char *allocate(std::ptrdiff_t n)
+    {
+        void *p = nullptr;
+        if (qbx_pool_malloc(&p, (size_t)n) != cudaSuccess) throw std::bad_alloc();
+        return (char *)p;
+    }
+    void deallocate(char *p, size_t) { qbx_pool_free_async(p); }
+};
+}   // namespace
+
+// Enqueue-only: nothing here waits for the device.  *d_nheavy (device, zeroed by the caller, may
+// be null) receives the number of chunks above QBX_HEAVY_TASK = the leading entries of the order.
 int qbx_chunk_order(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poff_bra,
-                    const int *poff_ket, int **order_out, int *nheavy_out, cudaStream_t s)
+                    const int *poff_ket, int **order_out, int *d_nheavy, cudaStream_t s)
 {
     *order_out = nullptr;
-    if (nheavy_out) *nheavy_out = 0;
     const int64_t nchunk = (n + 31) / 32;
     if (nchunk <= 1) return QBX_OK;
     float *cost = nullptr;
-    QBX_CUDA(cudaMalloc(&cost, nchunk * sizeof(float)));
-    QBX_CUDA(cudaMalloc(order_out, nchunk * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&cost, nchunk * sizeof(float)));
+    QBX_CUDA(qbx_dmalloc(order_out, nchunk * sizeof(int)));
     const int64_t threads = nchunk * 32;
-    k_chunk_cost<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(tasks, gt_bra, gt_grp, n, poff_bra, poff_ket, cost);
+    k_chunk_cost<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(tasks, gt_bra, gt_grp, n, poff_bra, poff_ket, cost, d_nheavy);
     QBX_CUDA(cudaGetLastError());
-    thrust::sequence(thrust::cuda::par.on(s), *order_out, *order_out + nchunk);
-    thrust::stable_sort_by_key(thrust::cuda::par.on(s), cost, cost + nchunk, *order_out, thrust::greater<float>());
-    if (nheavy_out)      // sorted descending: first position whose cost is not above the threshold
-        *nheavy_out = (int)(thrust::lower_bound(thrust::cuda::par.on(s), cost, cost + nchunk, QBX_HEAVY_TASK, thrust::greater<float>()) - cost);
-    QBX_CUDA(cudaStreamSynchronize(s));
-    cudaFree(cost);
+    try {
+        PoolAllocator alloc;
+        auto pol = thrust::cuda::par_nosync(alloc).on(s);
+        thrust::sequence(pol, *order_out, *order_out + nchunk);
+        thrust::stable_sort_by_key(pol, cost, cost + nchunk, *order_out, thrust::greater<float>());
+    } catch (const std::exception &e) {
+        qbx_set_error(std::string("chunk order: ") + e.what());
+        qbx_pool_free(cost);
+        return QBX_ERR_CUDA;
+    }
+    qbx_pool_free_async(cost);
     return QBX_OK;
 }
 
@@ -381,15 +445,15 @@ static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::
         }
     }
     out.la = la; out.lb = lb; out.npair = (int)sp.size(); out.nprim = poff.back();
-    QBX_CUDA(cudaMalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&out.soa_idx, std::max<size_t>(1, soa_idx.size()) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, soa_idx.size()) * sizeof(int2)));
     if (!soa.empty()) QBX_CUDA(cudaMemcpy(out.soa, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (!soa_idx.empty()) QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), soa_idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    QBX_CUDA(cudaMalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
-    QBX_CUDA(cudaMalloc(&out.prim_off, poff.size() * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&out.geom, std::max<size_t>(1, geom.size()) * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&out.prim, std::max<size_t>(1, prim.size()) * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&out.schwarz, std::max<size_t>(1, sp.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, geom.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, prim.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.schwarz, std::max<size_t>(1, sp.size()) * sizeof(double)));
     if (!sp.empty()) {
         QBX_CUDA(cudaMemcpy(out.shells, shells.data(), shells.size() * sizeof(int2), cudaMemcpyHostToDevice));
         QBX_CUDA(cudaMemcpy(out.geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -406,8 +470,8 @@ int Engine::upload(bool pair_adjacent)
     std::vector<double> sc(6 * ns);
     for (size_t s = 0; s < ns; ++s)
         for (int c = 0; c < 6; ++c) { bf[6 * s + c] = shells_[s].bf[c]; sc[6 * s + c] = shells_[s].scale[c]; }
-    QBX_CUDA(cudaMalloc(&d_shell_bf_, std::max<size_t>(1, bf.size()) * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&d_shell_scale_, std::max<size_t>(1, sc.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&d_shell_bf_, std::max<size_t>(1, bf.size()) * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&d_shell_scale_, std::max<size_t>(1, sc.size()) * sizeof(double)));
     QBX_CUDA(cudaMemcpy(d_shell_bf_, bf.data(), bf.size() * sizeof(int), cudaMemcpyHostToDevice));
     QBX_CUDA(cudaMemcpy(d_shell_scale_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<int> first(ns), ext;
@@ -416,8 +480,8 @@ int Engine::upload(bool pair_adjacent)
         for (int c = 0; c < qbx_nc(shells_[s].l); ++c) ext.push_back(shells_[s].bf[c]);
     }
     nint_ = (int64_t)ext.size();
-    QBX_CUDA(cudaMalloc(&d_shell_first_, std::max<size_t>(1, ns) * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&d_ext_of_int_, std::max<size_t>(1, ext.size()) * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&d_shell_first_, std::max<size_t>(1, ns) * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&d_ext_of_int_, std::max<size_t>(1, ext.size()) * sizeof(int)));
     QBX_CUDA(cudaMemcpy(d_shell_first_, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice));
     QBX_CUDA(cudaMemcpy(d_ext_of_int_, ext.data(), ext.size() * sizeof(int), cudaMemcpyHostToDevice));
     std::vector<std::pair<int, int>> sp[QBX_NPAIRCLS];
@@ -444,7 +508,7 @@ int Engine::upload(bool pair_adjacent)
             if (P.npair) QBX_CUDA(cudaMemcpy(sh.data(), P.shells, P.npair * sizeof(int2), cudaMemcpyDeviceToHost));
             std::vector<int4> info(P.npair);
             for (int i = 0; i < P.npair; ++i) info[i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
-            QBX_CUDA(cudaMalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
+            QBX_CUDA(qbx_dmalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
             if (P.npair) QBX_CUDA(cudaMemcpy(P.info, info.data(), info.size() * sizeof(int4), cudaMemcpyHostToDevice));
             // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
             if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
@@ -462,9 +526,9 @@ Engine::~Engine()
 {
     release_store();
     qbx_group_free(groups_);
-    for (auto &p : pairs_) { cudaFree(p.shells); cudaFree(p.prim_off); cudaFree(p.geom); cudaFree(p.prim); cudaFree(p.schwarz); cudaFree(p.soa); cudaFree(p.soa_idx); cudaFree(p.info); }
-    cudaFree(d_shell_bf_); cudaFree(d_shell_scale_); cudaFree(d_shell_first_); cudaFree(d_ext_of_int_); cudaFree(d_Dint_);
-    cudaFree(chunk_); cudaFree(d_Jt_); cudaFree(d_Kt_); cudaFree(d_counters_);
+    for (auto &p : pairs_) { qbx_pool_free(p.shells); qbx_pool_free(p.prim_off); qbx_pool_free(p.geom); qbx_pool_free(p.prim); qbx_pool_free(p.schwarz); qbx_pool_free(p.soa); qbx_pool_free(p.soa_idx); qbx_pool_free(p.info); }
+    qbx_pool_free(d_shell_bf_); qbx_pool_free(d_shell_scale_); qbx_pool_free(d_shell_first_); qbx_pool_free(d_ext_of_int_); qbx_pool_free(d_Dint_);
+    qbx_pool_free(chunk_); qbx_pool_free(d_Jt_); qbx_pool_free(d_Kt_); qbx_pool_free(d_counters_);
 
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     for (int i = 0; i < kSide; ++i) { if (side_[i]) cudaStreamDestroy(side_[i]); if (side_ev_[i]) cudaEventDestroy(side_ev_[i]); }
@@ -477,9 +541,9 @@ void Engine::release_store()
 {
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
-            cudaFree(tasks_[b][k].tasks); cudaFree(tasks_[b][k].gt_bra); cudaFree(tasks_[b][k].gt_grp); cudaFree(tasks_[b][k].gt_off); cudaFree(tasks_[b][k].order);
+            qbx_pool_free(tasks_[b][k].tasks); qbx_pool_free(tasks_[b][k].gt_bra); qbx_pool_free(tasks_[b][k].gt_grp); qbx_pool_free(tasks_[b][k].gt_off); qbx_pool_free(tasks_[b][k].order);
             tasks_[b][k] = TaskList();
-            cudaFree(vals_[b][k]); vals_[b][k] = nullptr;
+            qbx_pool_free(vals_[b][k]); vals_[b][k] = nullptr;
         }
     mode_ = -1;
     n_quartets_ = n_values_ = stored_bytes_ = 0;
@@ -508,7 +572,7 @@ int Engine::eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, 
     a.tasks = tasks; a.ntasks = n; a.out = out;
     a.shell_scale = d_shell_scale_;
     a.boys = qbx_boys_table();
-    if (!d_counters_) QBX_CUDA(cudaMalloc(&d_counters_, 1024 * sizeof(unsigned int)));
+    if (!d_counters_) QBX_CUDA(qbx_dmalloc(&d_counters_, 1024 * sizeof(unsigned int)));
     a.counter = d_counters_ + counter_next_;
     counter_next_ = (counter_next_ + 1) % 1024;
     QBX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), s));
@@ -543,8 +607,8 @@ int Engine::ensure_schwarz(cudaStream_t s)
         if (P.npair == 0) continue;
         const ClassOps *ops = qbx_class_ops(pc, pc);
         int2 *t = nullptr; double *v = nullptr;
-        QBX_CUDA(cudaMalloc(&t, P.npair * sizeof(int2)));
-        QBX_CUDA(cudaMalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&t, P.npair * sizeof(int2)));
+        QBX_CUDA(qbx_dmalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
         k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, s>>>(P.npair, t);
         int rc = run_eri(pc, pc, t, P.npair, v, s);
         if (rc) return rc;
@@ -552,50 +616,85 @@ int Engine::ensure_schwarz(cudaStream_t s)
         k_schwarz<<<(P.npair + 127) / 128, 128, 0, s>>>(v, P.npair, nab, P.schwarz);
         QBX_CUDA(cudaGetLastError());
         QBX_CUDA(cudaStreamSynchronize(s));
-        cudaFree(t); cudaFree(v);
+        qbx_pool_free(t); qbx_pool_free(v);
     }
     have_schwarz_ = true;
     return QBX_OK;
 }
 
-int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s)
+// Task lists are built in two enqueue-only phases so that a whole store needs two host
+// synchronisations instead of several per class:
+//   count: per-row counts -> device scan -> the total in d_total[0..2]
+//   fill : (the host has read the totals and sized the lists) compaction, statistics into
+//          d_stat[0..1] = (valid slots, primitive quartets), chunk order, heavy chunks into d_nheavy.
+int Engine::tasks_count(int bc, int kc, double tol, int rank, int nranks, bool grp, TaskScratch &ts, int64_t *d_total,
+                        cudaStream_t s)
+{
+    const DevPairSet &B = pairs_[bc], &K = pairs_[kc];
+    ts = TaskScratch();
+    if (B.npair == 0 || K.npair == 0) return QBX_OK;
+    if (grp) return qbx_group_count(groups_, B, K, bc == kc, tol, rank, nranks, ts, d_total, s);
+    QBX_CUDA(qbx_dmalloc(&ts.cnt[0], B.npair * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&ts.off[0], (B.npair + 1) * sizeof(int64_t)));
+    k_count_tasks<<<(unsigned)(((int64_t)B.npair * 32 + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, bc == kc,
+                                                                                 tol, ts.cnt[0]);
+    qbx_scan_counts(ts.cnt[0], B.npair, ts.off[0], d_total, s);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+
+int Engine::tasks_fill(int bc, int kc, double tol, int rank, int nranks, bool grp, bool want_order, TaskScratch &ts,
+                       const int64_t *h_total, TaskList &out, double *d_stat, int *d_nheavy, cudaStream_t s)
 {
     out = TaskList();
     const DevPairSet &B = pairs_[bc], &K = pairs_[kc];
+    int rc = QBX_OK;
     if (B.npair == 0 || K.npair == 0) return QBX_OK;
-    const int same = (bc == kc);
-    int *d_cnt = nullptr;
-    QBX_CUDA(cudaMalloc(&d_cnt, B.npair * sizeof(int)));
-    k_count_tasks<<<(B.npair + 127) / 128, 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol, d_cnt);
-    std::vector<int> cnt(B.npair);
-    QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, B.npair * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (grp) {
+        rc = qbx_group_fill(groups_, B, K, bc == kc, tol, rank, nranks, ts, h_total, out, d_stat, d_nheavy, s);
+    } else {
+        const int64_t total = h_total[0];
+        const int64_t nfull = total / QBX_TASK_CHUNK, rem = total % QBX_TASK_CHUNK;
+        int64_t mine = 0;
+        if (nfull > rank) mine = ((nfull - rank + nranks - 1) / nranks) * QBX_TASK_CHUNK;
+        if (rem && nfull % nranks == rank) mine += rem;
+        out.n = out.nvalid = mine;
+        if (mine > 0) {
+            QBX_CUDA(qbx_dmalloc(&out.tasks, mine * sizeof(int2)));
+            const int64_t threads = (int64_t)B.npair * 32;
+            k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, bc == kc, tol,
+                                                                           ts.off[0], rank, nranks, out.tasks);
+            k_task_cost<<<296, 256, 0, s>>>(out.tasks, mine, B.prim_off, K.prim_off, d_stat + 1);
+            QBX_CUDA(cudaGetLastError());
+            if (want_order) rc = qbx_chunk_order(out.tasks, nullptr, nullptr, mine, B.prim_off, K.prim_off, &out.order, nullptr, s);
+        }
+    }
+    for (int i = 0; i < 3; ++i) { qbx_pool_free_async(ts.cnt[i]); qbx_pool_free_async(ts.off[i]); }
+    ts = TaskScratch();
+    return rc;
+}
+
+// one class on its own (dense-tensor path): both phases with their synchronisations
+int Engine::build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s)
+{
+    out = TaskList();
+    if (pairs_[bc].npair == 0 || pairs_[kc].npair == 0) return QBX_OK;
+    char *h = (char *)qbx_pinned(64), *d = nullptr;
+    if (!h) { qbx_set_error("pinned scratch allocation failed"); return QBX_ERR_NOMEM; }
+    QBX_CUDA(qbx_dmalloc(&d, 64));
+    QBX_CUDA(cudaMemsetAsync(d, 0, 64, s));
+    TaskScratch ts;
+    int rc = tasks_count(bc, kc, tol, rank, nranks, false, ts, (int64_t *)d, s);
+    if (rc) return rc;
+    QBX_CUDA(cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, s));
     QBX_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_cnt);
-    std::vector<int64_t> rowoff(B.npair + 1, 0);
-    for (int i = 0; i < B.npair; ++i) rowoff[i + 1] = rowoff[i] + cnt[i];
-    const int64_t total = rowoff.back();
-    const int64_t nfull = total / QBX_TASK_CHUNK, rem = total % QBX_TASK_CHUNK;
-    int64_t mine = 0;
-    if (nfull > rank) mine = ((nfull - rank + nranks - 1) / nranks) * QBX_TASK_CHUNK;
-    if (rem && nfull % nranks == rank) mine += rem;
-    out.n = mine;
-    out.nvalid = mine;
-    if (mine == 0) return QBX_OK;
-    int64_t *d_off = nullptr;
-    QBX_CUDA(cudaMalloc(&d_off, rowoff.size() * sizeof(int64_t)));
-    QBX_CUDA(cudaMemcpyAsync(d_off, rowoff.data(), rowoff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    QBX_CUDA(cudaMalloc(&out.tasks, mine * sizeof(int2)));
-    const int64_t threads = (int64_t)B.npair * 32;
-    k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, same, tol,
-                                                                   d_off, rank, nranks, out.tasks);
-    QBX_CUDA(cudaGetLastError());
-    double *d_sum = nullptr;
-    QBX_CUDA(cudaMalloc(&d_sum, sizeof(double)));
-    QBX_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), s));
-    k_task_cost<<<296, 256, 0, s>>>(out.tasks, mine, B.prim_off, K.prim_off, d_sum);
-    QBX_CUDA(cudaMemcpyAsync(&out.nprimq, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    int64_t tot[3];
+    memcpy(tot, h, 24);
+    if ((rc = tasks_fill(bc, kc, tol, rank, nranks, false, false, ts, tot, out, (double *)(d + 24), nullptr, s))) return rc;
+    QBX_CUDA(cudaMemcpyAsync(h, d + 24, 16, cudaMemcpyDeviceToHost, s));
     QBX_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_off); cudaFree(d_sum);
+    out.nprimq = ((double *)h)[1];
+    qbx_pool_free_async(d);
     return QBX_OK;
 }
 
@@ -605,7 +704,7 @@ int Engine::fill_tensor(double *d_tensor, cudaStream_t s, double *stats)
 {
     int rc = ensure_schwarz(s);
     if (rc) return rc;
-    if (!chunk_) { QBX_CUDA(cudaMalloc(&chunk_, kChunkDoubles * sizeof(double))); chunk_doubles_ = kChunkDoubles; }
+    if (!chunk_) { QBX_CUDA(qbx_dmalloc(&chunk_, kChunkDoubles * sizeof(double))); chunk_doubles_ = kChunkDoubles; }
     for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
         for (int kc = 0; kc <= bc; ++kc) {
             TaskList tl;
@@ -622,58 +721,102 @@ int Engine::fill_tensor(double *d_tensor, cudaStream_t s, double *stats)
             }
             stats[3] += tl.nprimq;
             QBX_CUDA(cudaStreamSynchronize(s));
-            cudaFree(tl.tasks);
+            qbx_pool_free(tl.tasks);
         }
     return QBX_OK;
 }
 
 int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, double *stats)
 {
+    // QBX_TRACE=1: host-side phase times of this call on stderr (adds stream synchronisations)
+    const bool trace = getenv("QBX_TRACE") && atoi(getenv("QBX_TRACE"));
+    auto now = [&] { if (trace) cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    double t_tasks = 0, t_order = 0;
+    auto T0 = now();
     release_store();
     int rc = ensure_schwarz(s);
     if (rc) return rc;
-    for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
-        for (int kc = 0; kc <= bc; ++kc) {
-            if (mode == 0 && grouped(bc, kc))
-                rc = qbx_group_tasks(groups_, pairs_[bc], pairs_[kc], bc == kc, tol, rank, nranks, tasks_[bc][kc], s);
-            else
-                rc = build_tasks(bc, kc, tol, rank, nranks, tasks_[bc][kc], s);
-            if (rc) return rc;
-            if (mode == 0 && tasks_[bc][kc].ngt == 0 && tasks_[bc][kc].n > 0 &&
-                (rc = qbx_chunk_order(tasks_[bc][kc].tasks, nullptr, nullptr, tasks_[bc][kc].n, pairs_[bc].prim_off,
-                                      pairs_[kc].prim_off, &tasks_[bc][kc].order, nullptr, s)))
-                return rc;
-            const ClassOps *ops = qbx_class_ops(bc, kc);
-            const TaskList &tl = tasks_[bc][kc];
-            n_quartets_ += tl.nvalid;
-            n_values_ += tl.nvalid * ops->ncomp;
-            n_primq_ += tl.nprimq;
-            model_flops_ += tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
-                            (double)tl.nvalid * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
-            if (mode == 0 && tl.n > 0) {
-                const size_t bytes = (size_t)tl.n * ops->ncomp * sizeof(double);
-                if (cudaMalloc(&vals_[bc][kc], bytes) != cudaSuccess) {
-                    cudaGetLastError();
-                    qbx_set_error("qbx_eri_store: packed ERI store does not fit in device memory; use mode 1 (direct)");
-                    release_store();
-                    return QBX_ERR_NOMEM;
+    auto T1 = now();
+    // device scratch of the plan: totals[21][3] (int64), stats[21][2] (double), nheavy[21] (int)
+    const size_t o_stat = QBX_NCLASS * 3 * sizeof(int64_t), o_nh = o_stat + QBX_NCLASS * 2 * sizeof(double);
+    const size_t plan_bytes = o_nh + QBX_NCLASS * sizeof(int);
+    char *d_plan = nullptr, *h_plan = (char *)qbx_pinned(plan_bytes);
+    if (!h_plan) { qbx_set_error("pinned scratch allocation failed"); return QBX_ERR_NOMEM; }
+    QBX_CUDA(qbx_dmalloc(&d_plan, plan_bytes));
+    QBX_CUDA(cudaMemsetAsync(d_plan, 0, plan_bytes, s));
+    TaskScratch scratch[QBX_NCLASS];
+    {
+        int c = 0;
+        for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+            for (int kc = 0; kc <= bc; ++kc, ++c)
+                if ((rc = tasks_count(bc, kc, tol, rank, nranks, mode == 0 && grouped(bc, kc), scratch[c],
+                                      (int64_t *)d_plan + 3 * c, s)))
+                    return rc;
+    }
+    QBX_CUDA(cudaMemcpyAsync(h_plan, d_plan, o_stat, cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));                       // host sync 1 of 2: list sizes
+    int64_t totals[QBX_NCLASS * 3];
+    memcpy(totals, h_plan, o_stat);
+    auto T1b = now();
+    t_tasks = secs(T1, T1b);
+    {
+        int c = 0;
+        for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+            for (int kc = 0; kc <= bc; ++kc, ++c) {
+                if ((rc = tasks_fill(bc, kc, tol, rank, nranks, mode == 0 && grouped(bc, kc), mode == 0, scratch[c], totals + 3 * c,
+                                     tasks_[bc][kc], (double *)(d_plan + o_stat) + 2 * c, (int *)(d_plan + o_nh) + c, s)))
+                    return rc;
+                const TaskList &tl = tasks_[bc][kc];
+                if (mode == 0 && tl.n > 0) {
+                    const size_t bytes = (size_t)tl.n * qbx_class_ops(bc, kc)->ncomp * sizeof(double);
+                    if (qbx_dmalloc(&vals_[bc][kc], bytes) != cudaSuccess) {
+                        cudaGetLastError();
+                        qbx_set_error("qbx_eri_store: packed ERI store does not fit in device memory; use mode 1 (direct)");
+                        release_store();
+                        return QBX_ERR_NOMEM;
+                    }
+                    stored_bytes_ += (int64_t)bytes;
                 }
-                stored_bytes_ += (int64_t)bytes;
             }
-        }
+    }
+    QBX_CUDA(cudaMemcpyAsync(h_plan + o_stat, d_plan + o_stat, plan_bytes - o_stat, cudaMemcpyDeviceToHost, s));
+    QBX_CUDA(cudaStreamSynchronize(s));                       // host sync 2 of 2: statistics, heavy-chunk counts
+    qbx_pool_free_async(d_plan);
+    {
+        int c = 0;
+        for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
+            for (int kc = 0; kc <= bc; ++kc, ++c) {
+                TaskList &tl = tasks_[bc][kc];
+                const double *st = (const double *)(h_plan + o_stat) + 2 * c;
+                if (tl.ngt > 0) { tl.nvalid = (int64_t)st[0]; tl.nheavy = ((const int *)(h_plan + o_nh))[c]; }
+                tl.nprimq = st[1];
+                const ClassOps *ops = qbx_class_ops(bc, kc);
+                n_quartets_ += tl.nvalid;
+                n_values_ += tl.nvalid * ops->ncomp;
+                n_primq_ += tl.nprimq;
+                model_flops_ += tl.nprimq * qbx_model_flops_prim(ops->la, ops->lb, ops->lc, ops->ld) +
+                                (double)tl.nvalid * qbx_model_flops_hrr(ops->la, ops->lb, ops->lc, ops->ld);
+            }
+    }
+    t_order = secs(T1b, now());
+    auto T2 = now();
     if (!d_Jt_) {
-        QBX_CUDA(cudaMalloc(&d_Jt_, nint_ * nint_ * sizeof(double)));
-        QBX_CUDA(cudaMalloc(&d_Kt_, 2 * nint_ * nint_ * sizeof(double)));
-        QBX_CUDA(cudaMalloc(&d_Dint_, 3 * nint_ * nint_ * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&d_Jt_, nint_ * nint_ * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&d_Kt_, 2 * nint_ * nint_ * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&d_Dint_, 3 * nint_ * nint_ * sizeof(double)));
     }
     mode_ = mode;
     if (mode == 0) {
         if ((rc = recompute(s, stats))) return rc;
     } else if (!chunk_) {
-        QBX_CUDA(cudaMalloc(&chunk_, kChunkDoubles * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&chunk_, kChunkDoubles * sizeof(double)));
         chunk_doubles_ = kChunkDoubles;
     }
     QBX_CUDA(cudaStreamSynchronize(s));
+    if (trace)
+        fprintf(stderr, "qbx_eri_store: schwarz %.4f  count %.4f  fill+order+alloc %.4f  eri %.4f s\n", secs(T0, T1), t_tasks,
+                t_order, secs(T2, std::chrono::steady_clock::now()));
     return QBX_OK;
 }
 
@@ -855,8 +998,8 @@ int Engine::synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_
     int2 *d_t = nullptr; double *d_v = nullptr, *d_sum = nullptr;
     int rc = QBX_OK;
     do {
-        if (cudaMalloc(&d_t, nq * sizeof(int2)) != cudaSuccess || cudaMalloc(&d_v, (size_t)nq * ops->ncomp * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&d_sum, sizeof(double)) != cudaSuccess) { qbx_set_error("qbx_prim_batch: out of device memory"); rc = QBX_ERR_NOMEM; break; }
+        if (qbx_dmalloc(&d_t, nq * sizeof(int2)) != cudaSuccess || qbx_dmalloc(&d_v, (size_t)nq * ops->ncomp * sizeof(double)) != cudaSuccess ||
+            qbx_dmalloc(&d_sum, sizeof(double)) != cudaSuccess) { qbx_set_error("qbx_prim_batch: out of device memory"); rc = QBX_ERR_NOMEM; break; }
         cudaMemcpyAsync(d_t, tasks.data(), nq * sizeof(int2), cudaMemcpyHostToDevice, s);
         if ((rc = e->run_eri(bc, kc, d_t, nq, d_v, s))) break;           // warm-up
         cudaEventRecord(e->ev0_, s);
@@ -885,7 +1028,7 @@ int Engine::synthetic(int la, int lb, int lc, int ld, int K, int64_t nq, uint64_
             }
         }
     } while (0);
-    cudaFree(d_t); cudaFree(d_v); cudaFree(d_sum);
+    qbx_pool_free(d_t); qbx_pool_free(d_v); qbx_pool_free(d_sum);
     delete e;
     return rc;
 }

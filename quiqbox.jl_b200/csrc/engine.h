@@ -68,9 +68,17 @@ struct TaskList {
     int *order = nullptr;                // 32-task chunks sorted by cost, heaviest first (LPT schedule for the work queue)
     int nheavy = 0;                      // leading chunks of `order` whose tasks exceed QBX_HEAVY_TASK primitive quartets
 };
-// cost-sorted chunk order of a task list (tasks != null) or of a group-task list (tasks == null)
+// device scratch of one class between the count and the fill phase of task building
+struct TaskScratch {
+    int *cnt[3] = {nullptr, nullptr, nullptr};
+    int64_t *off[3] = {nullptr, nullptr, nullptr};
+};
+// cost-sorted chunk order of a task list (tasks != null) or of a group-task list (tasks == null);
+// enqueue-only, *d_nheavy (device) += chunks above QBX_HEAVY_TASK
 int qbx_chunk_order(const int2 *tasks, const int *gt_bra, const int *gt_grp, int64_t n, const int *poff_bra,
-                    const int *poff_ket, int **order_out, int *nheavy_out, cudaStream_t s);
+                    const int *poff_ket, int **order_out, int *d_nheavy, cudaStream_t s);
+// off[i] = exclusive prefix sum of cnt, off[n] = *d_total = the sum (enqueue-only)
+void qbx_scan_counts(const int *cnt, int n, int64_t *off, int64_t *d_total, cudaStream_t s);
 #define QBX_HEAVY_TASK 1024.0f
 
 // (ss) group pairs: ket-side general-contraction sharing, see eri_group.cu
@@ -83,8 +91,13 @@ struct GroupSet {
 };
 int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out);
 void qbx_group_free(GroupSet &g);
-int qbx_group_tasks(const GroupSet &G, const struct DevPairSet &B, const struct DevPairSet &K, bool same, double tol, int rank,
-                    int nranks, TaskList &tl, cudaStream_t s);
+// two enqueue-only phases, see Engine::tasks_count / tasks_fill.  d_total[0..2] = group tasks of all
+// ranks, group tasks of this rank, slots of this rank.
+int qbx_group_count(const GroupSet &G, const struct DevPairSet &B, const struct DevPairSet &K, bool same, double tol, int rank,
+                    int nranks, TaskScratch &ts, int64_t *d_total, cudaStream_t s);
+int qbx_group_fill(const GroupSet &G, const struct DevPairSet &B, const struct DevPairSet &K, bool same, double tol, int rank,
+                   int nranks, TaskScratch &ts, const int64_t *h_total, TaskList &tl, double *d_stat, int *d_nheavy,
+                   cudaStream_t s);
 int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList &tl, cudaStream_t s);
 
 class Engine {
@@ -111,6 +124,9 @@ private:
     int upload(bool pair_adjacent);
     int ensure_schwarz(cudaStream_t s);
     int build_tasks(int bc, int kc, double tol, int rank, int nranks, TaskList &out, cudaStream_t s);
+    int tasks_count(int bc, int kc, double tol, int rank, int nranks, bool grp, TaskScratch &ts, int64_t *d_total, cudaStream_t s);
+    int tasks_fill(int bc, int kc, double tol, int rank, int nranks, bool grp, bool want_order, TaskScratch &ts,
+                   const int64_t *h_total, TaskList &out, double *d_stat, int *d_nheavy, cudaStream_t s);
     int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, const int *order = nullptr);
     int eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a);
     bool grouped(int bc, int kc) const { return use_groups_ && kc == 0 && (bc == 0 || bc == 1); }   // (ss|ss), (ps|ss); (ds|ss) measured slower

@@ -354,11 +354,11 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         base += gs * np * QBX_GRP_NF;
         g0 = g1;
     }
-    QBX_CUDA(cudaMalloc(&out.nmem, std::max<size_t>(1, ng0) * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&out.members, std::max<size_t>(1, mem.size()) * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&out.prim_off, poff.size() * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
-    QBX_CUDA(cudaMalloc(&out.soa_idx, std::max<size_t>(1, ng0) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&out.nmem, std::max<size_t>(1, ng0) * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.members, std::max<size_t>(1, mem.size()) * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, ng0) * sizeof(int2)));
     if (ng0) {
         QBX_CUDA(cudaMemcpy(out.nmem, out.h_nmem.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice));
         QBX_CUDA(cudaMemcpy(out.members, mem.data(), mem.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -371,60 +371,48 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
 
 void qbx_group_free(GroupSet &g)
 {
-    cudaFree(g.nmem); cudaFree(g.members); cudaFree(g.prim_off); cudaFree(g.soa); cudaFree(g.soa_idx);
+    qbx_pool_free(g.nmem); qbx_pool_free(g.members); qbx_pool_free(g.prim_off); qbx_pool_free(g.soa); qbx_pool_free(g.soa_idx);
     g = GroupSet();
 }
 
 // Builds the slot list (tl.tasks / tl.n) and the group tasks of one (x s|ss) class for this rank.
-int qbx_group_tasks(const GroupSet &G, const DevPairSet &B, const DevPairSet &K, bool same, double tol, int rank, int nranks,
-                    TaskList &tl, cudaStream_t s)
+int qbx_group_count(const GroupSet &G, const DevPairSet &B, const DevPairSet &K, bool same, double tol, int rank, int nranks,
+                    TaskScratch &ts, int64_t *d_total, cudaStream_t s)
+{
+    if (B.npair == 0 || G.ng == 0) return QBX_OK;
+    const int nb = B.npair, grid = (nb + 127) / 128;
+    for (int i = 0; i < 3; ++i) {
+        QBX_CUDA(qbx_dmalloc(&ts.cnt[i], nb * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&ts.off[i], (nb + 1) * sizeof(int64_t)));
+    }
+    k_gcount<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, ts.cnt[0]);
+    qbx_scan_counts(ts.cnt[0], nb, ts.off[0], d_total, s);
+    k_gcount_owned<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, ts.off[0], rank, nranks,
+                                        ts.cnt[1], ts.cnt[2]);
+    qbx_scan_counts(ts.cnt[1], nb, ts.off[1], d_total + 1, s);
+    qbx_scan_counts(ts.cnt[2], nb, ts.off[2], d_total + 2, s);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+
+int qbx_group_fill(const GroupSet &G, const DevPairSet &B, const DevPairSet &K, bool same, double tol, int rank, int nranks,
+                   TaskScratch &ts, const int64_t *h_total, TaskList &tl, double *d_stat, int *d_nheavy, cudaStream_t s)
 {
     tl = TaskList();
     if (B.npair == 0 || G.ng == 0) return QBX_OK;
     const int nb = B.npair, grid = (nb + 127) / 128;
-    int *d_c0 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
-    int64_t *d_o0 = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
-    QBX_CUDA(cudaMalloc(&d_c0, nb * sizeof(int))); QBX_CUDA(cudaMalloc(&d_c1, nb * sizeof(int))); QBX_CUDA(cudaMalloc(&d_c2, nb * sizeof(int)));
-    QBX_CUDA(cudaMalloc(&d_o0, (nb + 1) * sizeof(int64_t))); QBX_CUDA(cudaMalloc(&d_o1, (nb + 1) * sizeof(int64_t)));
-    QBX_CUDA(cudaMalloc(&d_o2, (nb + 1) * sizeof(int64_t)));
-    std::vector<int> c0(nb), c1(nb), c2(nb);
-    std::vector<int64_t> o0(nb + 1, 0), o1(nb + 1, 0), o2(nb + 1, 0);
-    k_gcount<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, d_c0);
-    QBX_CUDA(cudaMemcpyAsync(c0.data(), d_c0, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-    QBX_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < nb; ++i) o0[i + 1] = o0[i] + c0[i];
-    QBX_CUDA(cudaMemcpyAsync(d_o0, o0.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    k_gcount_owned<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, d_o0, rank, nranks, d_c1, d_c2);
-    QBX_CUDA(cudaMemcpyAsync(c1.data(), d_c1, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-    QBX_CUDA(cudaMemcpyAsync(c2.data(), d_c2, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-    QBX_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < nb; ++i) { o1[i + 1] = o1[i] + c1[i]; o2[i + 1] = o2[i] + c2[i]; }
-    tl.ngt = (int)o1[nb];
-    tl.n = o2[nb];
-    if (tl.ngt > 0) {
-        QBX_CUDA(cudaMemcpyAsync(d_o1, o1.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        QBX_CUDA(cudaMemcpyAsync(d_o2, o2.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        QBX_CUDA(cudaMalloc(&tl.tasks, tl.n * sizeof(int2)));
-        QBX_CUDA(cudaMalloc(&tl.gt_bra, tl.ngt * sizeof(int)));
-        QBX_CUDA(cudaMalloc(&tl.gt_grp, tl.ngt * sizeof(int)));
-        QBX_CUDA(cudaMalloc(&tl.gt_off, tl.ngt * sizeof(int)));
-        k_gfill<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, d_o0, rank, nranks, d_o1, d_o2,
-                                     tl.gt_bra, tl.gt_grp, tl.gt_off, tl.tasks);
-        QBX_CUDA(cudaGetLastError());
-        double *d_st = nullptr, st[2] = {0, 0};
-        QBX_CUDA(cudaMalloc(&d_st, 2 * sizeof(double)));
-        QBX_CUDA(cudaMemsetAsync(d_st, 0, 2 * sizeof(double), s));
-        k_gstats<<<296, 256, 0, s>>>(tl.tasks, tl.n, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, d_st);
-        QBX_CUDA(cudaMemcpyAsync(st, d_st, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        QBX_CUDA(cudaStreamSynchronize(s));
-        cudaFree(d_st);
-        tl.nvalid = (int64_t)st[0];
-        tl.nprimq = st[1];
-        int rc = qbx_chunk_order(nullptr, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, &tl.order, &tl.nheavy, s);
-        if (rc) return rc;
-    }
-    cudaFree(d_c0); cudaFree(d_c1); cudaFree(d_c2); cudaFree(d_o0); cudaFree(d_o1); cudaFree(d_o2);
-    return QBX_OK;
+    tl.ngt = (int)h_total[1];
+    tl.n = h_total[2];
+    if (tl.ngt <= 0) { tl.ngt = 0; tl.n = 0; return QBX_OK; }
+    QBX_CUDA(qbx_dmalloc(&tl.tasks, tl.n * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&tl.gt_bra, tl.ngt * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&tl.gt_grp, tl.ngt * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&tl.gt_off, tl.ngt * sizeof(int)));
+    k_gfill<<<grid, 128, 0, s>>>(B.schwarz, K.schwarz, nb, same, tol, G.ng, G.members, G.nmem, ts.off[0], rank, nranks, ts.off[1],
+                                 ts.off[2], tl.gt_bra, tl.gt_grp, tl.gt_off, tl.tasks);
+    k_gstats<<<296, 256, 0, s>>>(tl.tasks, tl.n, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, d_stat);
+    QBX_CUDA(cudaGetLastError());
+    return qbx_chunk_order(nullptr, tl.gt_bra, tl.gt_grp, tl.ngt, B.prim_off, G.prim_off, &tl.order, d_nheavy, s);
 }
 
 int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList &tl, cudaStream_t s)

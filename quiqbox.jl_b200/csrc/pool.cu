@@ -1,0 +1,124 @@
+// Device-memory pool of libqbx.so.
+//
+// Every step of the reference's workflow (one geometry of a scan, one SCF of an optimisation,
+// src/HartreeFock.jl:583-606) builds a new basis, a new ERI store of the same few sizes, and
+// drops them again.  cudaMalloc/cudaFree of the ~10 GB packed store cost 0.1-0.7 s per step on
+// B200 (page mapping + the implicit device synchronisation of cudaFree) -- several times the
+// 32 ms the ERI kernels need -- so freed blocks are kept here, keyed by size, and handed out again.
+//   QBX_POOL_GB=<n>  upper bound of cached (not in use) bytes, default 64; 0 switches pooling off.
+// qbx_pool_trim() / qbx_shutdown() give everything back to the driver.
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
+#include "qbx_internal.h"
+
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void *> idle;              // size -> block
+    std::unordered_map<void *, size_t> size_of;      // every block that came from qbx_pool_malloc
+    size_t idle_bytes = 0, cap = 0;
+    bool cap_read = false;
+    int64_t hits = 0, misses = 0;
+};
+Pool g_pool;
+
+size_t pool_cap(Pool &P)
+{
+    if (!P.cap_read) {
+        const char *e = getenv("QBX_POOL_GB");
+        const double gb = e ? atof(e) : 64.0;
+        P.cap = gb <= 0 ? 0 : (size_t)(gb * (double)(1ull << 30));
+        P.cap_read = true;
+    }
+    return P.cap;
+}
+
+void release_idle(Pool &P)
+{
+    for (auto &kv : P.idle) { P.size_of.erase(kv.second); cudaFree(kv.second); }
+    P.idle.clear();
+    P.idle_bytes = 0;
+}
+}   // namespace
+
+cudaError_t qbx_pool_malloc(void **p, size_t bytes)
+{
+    Pool &P = g_pool;
+    const size_t sz = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (pool_cap(P)) {
+        auto it = P.idle.lower_bound(sz);
+        // a block is reused when it wastes at most a quarter of itself (or less than 1 MiB)
+        if (it != P.idle.end() && (it->first - sz <= (1u << 20) || it->first - sz <= it->first / 4)) {
+            *p = it->second;
+            P.idle_bytes -= it->first;
+            P.idle.erase(it);
+            ++P.hits;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, sz);
+    if (e != cudaSuccess && !P.idle.empty()) {       // give the cache back and try again
+        cudaGetLastError();
+        release_idle(P);
+        e = cudaMalloc(p, sz);
+    }
+    if (e == cudaSuccess) { P.size_of[*p] = sz; ++P.misses; }
+    return e;
+}
+
+static cudaError_t pool_free(void *p, bool sync)
+{
+    if (!p) return cudaSuccess;
+    Pool &P = g_pool;
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.size_of.find(p);
+    if (it == P.size_of.end()) return cudaFree(p);    // not ours
+    const size_t sz = it->second;
+    if (pool_cap(P) == 0 || P.idle_bytes + sz > P.cap) {
+        P.size_of.erase(it);
+        return cudaFree(p);
+    }
+    cudaError_t e = sync ? cudaDeviceSynchronize() : cudaSuccess;
+    P.idle.emplace(sz, p);
+    P.idle_bytes += sz;
+    return e;
+}
+
+// same contract as cudaFree: work that still uses the block has finished when this returns
+cudaError_t qbx_pool_free(void *p) { return pool_free(p, true); }
+
+// Stream-ordered variant for scratch blocks: the caller guarantees that every later user of the
+// block is ordered after the work enqueued so far.  That holds inside the library because all of
+// it runs on the library's one stream (side streams fork from and join into it) and
+// qbx_set_stream synchronises the device when the stream changes.
+cudaError_t qbx_pool_free_async(void *p) { return pool_free(p, false); }
+
+// Pinned host scratch for the small read-backs (counts, totals); grows, never shrinks.
+void *qbx_pinned(size_t bytes)
+{
+    static void *buf = nullptr;
+    static size_t cap = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = std::max<size_t>(bytes, 1 << 16);
+        if (cudaMallocHost(&buf, cap) != cudaSuccess) { cudaGetLastError(); buf = nullptr; cap = 0; }
+    }
+    return buf;
+}
+
+void qbx_pool_release()
+{
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    release_idle(g_pool);
+}
+
+void qbx_pool_counts(int64_t *hits, int64_t *misses, int64_t *idle_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    *hits = g_pool.hits; *misses = g_pool.misses; *idle_bytes = (int64_t)g_pool.idle_bytes;
+}

@@ -26,6 +26,15 @@ void qbx_set_error(const std::string &msg);
         }                                                                                     \
     } while (0)
 
+// pool.cu: device allocations of the library go through a size-keyed pool
+cudaError_t qbx_pool_malloc(void **p, size_t bytes);
+cudaError_t qbx_pool_free(void *p);
+cudaError_t qbx_pool_free_async(void *p);
+void *qbx_pinned(size_t bytes);
+void qbx_pool_release();
+void qbx_pool_counts(int64_t *hits, int64_t *misses, int64_t *idle_bytes);
+template <class T> inline cudaError_t qbx_dmalloc(T **p, size_t bytes) { return qbx_pool_malloc((void **)p, bytes); }
+
 __host__ __device__ constexpr int qbx_nc(int l) { return (l + 1) * (l + 2) / 2; }
 
 // flat primitive table + CSR on the device (generic kernels)

@@ -28,6 +28,7 @@ SIGNATURES = {
     "qbx_set_stream": [C.c_void_p],
     "qbx_class_stats": [C.c_void_p, C.c_void_p],
     "qbx_fp64_peak": [C.c_void_p],
+    "qbx_pool_trim": [C.c_void_p],
     "qbx_fock_build": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_fock_build_device": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "qbx_one_body": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
