@@ -35,6 +35,7 @@ static int launch_eri(const ClassArgs &a, cudaStream_t s)
 static int launch_digest(const DigestArgs &a, cudaStream_t s)
 {
     if (a.ntasks <= 0) return QBX_OK;
+    if (a.ntasks > (int64_t)128 * 0x7fffffff) { qbx_set_error("digest: task list too long for one launch"); return QBX_ERR_ARG; }
     const int64_t nblk = (a.ntasks + 127) / 128;
     const int64_t R = nblk < a.spread ? nblk : a.spread, C = (nblk + R - 1) / R;
     digest_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(R * C), 128, 0, s>>>(a);

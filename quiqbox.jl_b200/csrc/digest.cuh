@@ -35,31 +35,56 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Latency notes (ncu, profiles/r01): the kernel is bound by exposed memory latency, not by
-// any throughput, so the body is organised as few dependent steps as possible:
-//   task -> one int4 record per pair (shells + first function indices) -> all densities and
-//   the values of one (a,b) slice as independent loads -> FMAs -> all shuffles/REDs at the end.
+// K updates of one bra-side function x (= a or b) against the ket functions: K[x c] is one address
+// per warp when the warp shares C (shuffle reduction, one RED), K[x d] is consecutive over the lanes.
+template <int NCc, int ND>
+__device__ __forceinline__ void digest_flush_row(double *Kt, int N, int ix, int ic, int id, const double *kxc,
+                                                 const double *kxd, double f, bool uniC, bool valid, bool lane0)
+{
+#pragma unroll
+    for (int c = 0; c < NCc; ++c) {
+        double x = f * kxc[c];
+        if (uniC) {
+            x = warp_sum(x);
+            if (lane0) atomicAdd(Kt + (ic + c) + N * ix, x);
+        } else if (valid) {
+            atomicAdd(Kt + (ic + c) + N * ix, x);
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) atomicAdd(Kt + (id + d) + N * ix, f * kxd[d]);
+    }
+}
+
+// Kernel structure (ncu, profiles/r01: nothing is saturated, the kernel waits on memory):
+//   * the values of a quartet do not depend on its task record, so the first slab of value loads
+//     is issued before anything else and overlaps the chain task -> pair info -> densities;
+//   * values are consumed in slabs of up to 64 independent loads (whole quartet, one `a`, or one
+//     (a,b) slice) -- the bytes in flight per SM are what decides the HBM rate here;
+//   * accumulators of row a (K[ac], K[ad]) are flushed as soon as a is finished, those of row b
+//     stay in registers only when they are few (QBX_DIGEST_KEEP_B), so that no class spills;
+//   * the block factor f multiplies the sums at flush time, not the values.
 // Values are read once and feed J and K together (the second exchange density of a UHF build
 // re-reads them).
-template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
+#define QBX_DIGEST_SLAB 64
+#define QBX_DIGEST_KEEP_B 18
+
+// resident blocks per SM the register allocation aims at (128 threads each)
+__host__ __device__ constexpr int digest_min_blocks(int ncomp)
+{
+    return ncomp <= 3 ? 10 : (ncomp <= 9 ? 6 : (ncomp <= 36 ? 4 : (ncomp <= 162 ? 3 : 2)));
+}
+
+// J/K updates of one quartet per lane.  v holds slab 0 of the quartet's values on entry.
+template <int LA, int LB, int LC, int LD, int SL, bool PV>
+__device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double *__restrict__ vq, bool valid, int2 t, int4 rb,
+                                               int4 rk, double (&v)[SL * NC(LC) * NC(LD)])
 {
     constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NCD = NCc * ND;
-    // Block order is transposed against task order: the blocks resident at one time sit
-    // spread-th of the list apart, i.e. on different bra rows.  In task order they would
-    // all update the same few hundred G elements, and fp64 REDs on a hot set that small run at
-    // 1e10/s instead of 2e11/s on B200 (tools/redbench.cu; profiles/r01/redbench.md).
-    const int64_t nblk = (p.ntasks + 127) / 128;
-    const int64_t R = nblk < p.spread ? nblk : p.spread, C = (nblk + R - 1) / R;
-    const int64_t blk = (blockIdx.x % R) * C + blockIdx.x / R;
-    if (blk >= nblk) return;
-    const int64_t q0 = blk * 128 + threadIdx.x;
-    if (q0 - (threadIdx.x & 31) >= p.ntasks) return;          // whole warp past the end
-    const int64_t q = q0 < p.ntasks ? q0 : p.ntasks - 1;
-    int2 t = p.tasks[q];
-    const bool valid = q0 < p.ntasks && t.y >= 0;              // ket = -1: unused slot of a group task
-    if (t.y < 0) t.y = 0;
-    const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);   // (shell A, shell B, first A, first B)
+    constexpr bool KEEP_B = NB * (NCc + ND) <= QBX_DIGEST_KEEP_B;     // K[bc], K[bd] live across a
+    constexpr bool KEEP_DCD = NCD <= 18;                              // D[cd] in registers
+    const int64_t nt = p.ntasks;
     double f = valid ? 1.0 : 0.0;
     if (rb.x == rb.y) f *= 0.5;
     if (rk.x == rk.y) f *= 0.5;
@@ -67,65 +92,71 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
     const bool uniAB = __all_sync(0xffffffffu, t.x == __shfl_sync(0xffffffffu, t.x, 0));
     const bool uniC = uniAB && __all_sync(0xffffffffu, rk.x == __shfl_sync(0xffffffffu, rk.x, 0));
     const bool lane0 = (threadIdx.x & 31) == 0;
-    const int64_t N = p.nbf;                                  // internal dimension
+    const int N = p.nbf;                                      // internal dimension
     const int ia = rb.z, ib = rb.w, ic = rk.z, id = rk.w;
-    const double *vq = p.vals + q;
+    const double *__restrict__ DJ = p.DJ;
 
     for (int m = 0; m < p.nmat; ++m) {
-        const double *DK = p.DK + m * N * N;
-        double *Kt = p.Kt + m * N * N;
+        const double *__restrict__ DK = p.DK + (int64_t)m * N * N;
+        double *Kt = p.Kt + (int64_t)m * N * N;
         const bool coul = (m == 0);
-        double dcd[NCD], jcd[NCD], jab[NA * NB];
-        double dac[NA * NCc], dad[NA * ND], dbc[NB * NCc], dbd[NB * ND];
-        double kac[NA * NCc], kad[NA * ND], kbc[NB * NCc], kbd[NB * ND];
+        double dcd[KEEP_DCD ? NCD : 1], jcd[NCD];
+        double dbc[KEEP_B ? NB * NCc : NCc], dbd[KEEP_B ? NB * ND : ND], kbc[KEEP_B ? NB * NCc : NCc], kbd[KEEP_B ? NB * ND : ND];
 #pragma unroll
-        for (int c = 0; c < NCc; ++c)
+        for (int cd = 0; cd < NCD; ++cd) jcd[cd] = 0.0;
+        if (KEEP_DCD) {
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { dcd[c * ND + d] = coul ? p.DJ[(id + d) + N * (ic + c)] : 0.0; jcd[c * ND + d] = 0.0; }
+            for (int c = 0; c < NCc; ++c)
 #pragma unroll
-        for (int a = 0; a < NA; ++a) {
-#pragma unroll
-            for (int c = 0; c < NCc; ++c) { dac[a * NCc + c] = DK[(ic + c) + N * (ia + a)]; kac[a * NCc + c] = 0.0; }
-#pragma unroll
-            for (int d = 0; d < ND; ++d) { dad[a * ND + d] = DK[(id + d) + N * (ia + a)]; kad[a * ND + d] = 0.0; }
+                for (int d = 0; d < ND; ++d) dcd[c * ND + d] = coul ? DJ[(id + d) + N * (ic + c)] : 0.0;
         }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int c = 0; c < NCc; ++c) { dbc[b * NCc + c] = DK[(ic + c) + N * (ib + b)]; kbc[b * NCc + c] = 0.0; }
-#pragma unroll
-            for (int d = 0; d < ND; ++d) { dbd[b * ND + d] = DK[(id + d) + N * (ib + b)]; kbd[b * ND + d] = 0.0; }
-        }
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
+        if (KEEP_B) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const double dab = coul ? p.DJ[(ib + b) + N * (ia + a)] : 0.0;
-                double v[NCD];
 #pragma unroll
-                for (int cd = 0; cd < NCD; ++cd) v[cd] = f * vq[(int64_t)((a * NB + b) * NCD + cd) * p.ntasks];
+                for (int c = 0; c < NCc; ++c) { dbc[b * NCc + c] = DK[(ic + c) + N * (ib + b)]; kbc[b * NCc + c] = 0.0; }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { dbd[b * ND + d] = DK[(id + d) + N * (ib + b)]; kbd[b * ND + d] = 0.0; }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            double dac[NCc], dad[ND], kac[NCc], kad[ND];
+#pragma unroll
+            for (int c = 0; c < NCc; ++c) { dac[c] = DK[(ic + c) + N * (ia + a)]; kac[c] = 0.0; }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { dad[d] = DK[(id + d) + N * (ia + a)]; kad[d] = 0.0; }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int ab = a * NB + b, s0 = (ab % SL) * NCD;
+                if (ab % SL == 0 && (!PV || ab > 0 || m > 0)) {      // next slab of values
+#pragma unroll
+                    for (int i = 0; i < SL * NCD; ++i) v[i] = __ldg(vq + (int64_t)(ab * NCD + i) * nt);
+                }
+                const int ob = KEEP_B ? b : 0;
+                if (!KEEP_B) {
+#pragma unroll
+                    for (int c = 0; c < NCc; ++c) { dbc[c] = DK[(ic + c) + N * (ib + b)]; kbc[c] = 0.0; }
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { dbd[d] = DK[(id + d) + N * (ib + b)]; kbd[d] = 0.0; }
+                }
+                const double dab = coul ? DJ[(ib + b) + N * (ia + a)] : 0.0;
                 double j = 0.0;
 #pragma unroll
                 for (int c = 0; c < NCc; ++c)
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
-                        const double x = v[c * ND + d];
-                        j = fma(dcd[c * ND + d], x, j);
+                        const double x = v[s0 + c * ND + d];
+                        const double dd = KEEP_DCD ? dcd[c * ND + d] : (coul ? DJ[(id + d) + N * (ic + c)] : 0.0);
+                        j = fma(dd, x, j);
                         jcd[c * ND + d] = fma(dab, x, jcd[c * ND + d]);
-                        kac[a * NCc + c] = fma(dbd[b * ND + d], x, kac[a * NCc + c]);
-                        kad[a * ND + d] = fma(dbc[b * NCc + c], x, kad[a * ND + d]);
-                        kbc[b * NCc + c] = fma(dad[a * ND + d], x, kbc[b * NCc + c]);
-                        kbd[b * ND + d] = fma(dac[a * NCc + c], x, kbd[b * ND + d]);
+                        kac[c] = fma(dbd[ob * ND + d], x, kac[c]);
+                        kad[d] = fma(dbc[ob * NCc + c], x, kad[d]);
+                        kbc[ob * NCc + c] = fma(dad[d], x, kbc[ob * NCc + c]);
+                        kbd[ob * ND + d] = fma(dac[c], x, kbd[ob * ND + d]);
                     }
-                jab[a * NB + b] = j;
-            }
-        // ---- updates (f is already folded into the values)
-        if (coul) {
-#pragma unroll
-            for (int a = 0; a < NA; ++a)
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    double j = 2.0 * jab[a * NB + b];
+                if (coul) {                                   // J[ab]: one address per warp
+                    j *= 2.0 * f;
                     if (uniAB) {
                         j = warp_sum(j);
                         if (lane0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
@@ -133,49 +164,54 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestArgs p)
                         atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
                     }
                 }
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < NCc; ++c)
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) atomicAdd(p.Jt + (id + d) + N * (ic + c), 2.0 * jcd[c * ND + d]);
+                if (!KEEP_B) digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc, kbd, f, uniC, valid, lane0);
             }
+            digest_flush_row<NCc, ND>(Kt, N, ia + a, ic, id, kac, kad, f, uniC, valid, lane0);
         }
-        if (uniC) {                                           // K[ac], K[bc]: one address per warp
-#pragma unroll
-            for (int a = 0; a < NA; ++a)
-#pragma unroll
-                for (int c = 0; c < NCc; ++c) {
-                    const double x = warp_sum(kac[a * NCc + c]);
-                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ia + a), x);
-                }
+        if (KEEP_B) {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int c = 0; c < NCc; ++c) {
-                    const double x = warp_sum(kbc[b * NCc + c]);
-                    if (lane0) atomicAdd(Kt + (ic + c) + N * (ib + b), x);
-                }
-        } else if (valid) {
-#pragma unroll
-            for (int a = 0; a < NA; ++a)
-#pragma unroll
-                for (int c = 0; c < NCc; ++c) atomicAdd(Kt + (ic + c) + N * (ia + a), kac[a * NCc + c]);
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int c = 0; c < NCc; ++c) atomicAdd(Kt + (ic + c) + N * (ib + b), kbc[b * NCc + c]);
+                digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc + b * NCc, kbd + b * ND, f, uniC, valid, lane0);
         }
-        if (valid) {                                          // K[ad], K[bd]: consecutive over the lanes
+        if (coul && valid) {                                  // J[cd]: consecutive over the lanes
 #pragma unroll
-            for (int a = 0; a < NA; ++a)
+            for (int c = 0; c < NCc; ++c)
 #pragma unroll
-                for (int d = 0; d < ND; ++d) atomicAdd(Kt + (id + d) + N * (ia + a), kad[a * ND + d]);
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int d = 0; d < ND; ++d) atomicAdd(Kt + (id + d) + N * (ib + b), kbd[b * ND + d]);
+                for (int d = 0; d < ND; ++d) atomicAdd(p.Jt + (id + d) + N * (ic + c), 2.0 * f * jcd[c * ND + d]);
         }
     }
+}
+
+// (A three-stage register pipeline over several tiles per block -- task records of tile i+2, pair
+// info and values of tile i+1 in flight while tile i is digested -- was measured and is not
+// faster: 13.9 ms against 13.1 ms for the whole (H2O)16 build.  The kernel is bound by the L2
+// RED rate and the L1TEX request rate of the density gathers, not by the latency chain.)
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(128, digest_min_blocks(NC(LA) * NC(LB) * NC(LC) * NC(LD))) digest_kernel(DigestArgs p)
+{
+    constexpr int NA = NC(LA), NB = NC(LB), NCD = NC(LC) * NC(LD), NAB = NA * NB;
+    // (a,b) slices per slab of value loads
+    constexpr int SL = (NAB * NCD <= QBX_DIGEST_SLAB) ? NAB : ((NB * NCD <= QBX_DIGEST_SLAB) ? NB : 1);
+    // Block order is transposed against task order: the blocks resident at one time sit
+    // spread-th of the list apart, i.e. on different bra rows.  In task order they would
+    // all update the same few hundred G elements, and fp64 REDs on a hot set that small run at
+    // 1e10/s instead of 2e11/s on B200 (tools/redbench.cu; profiles/r01/redbench.md).
+    const unsigned nblk = (unsigned)((p.ntasks + 127) / 128);
+    const unsigned R = nblk < (unsigned)p.spread ? nblk : (unsigned)p.spread, C = (nblk + R - 1) / R;
+    const unsigned blk = (blockIdx.x % R) * C + blockIdx.x / R;
+    if (blk >= nblk) return;
+    const int64_t q0 = (int64_t)blk * 128 + threadIdx.x;
+    if (q0 - (threadIdx.x & 31) >= p.ntasks) return;          // whole warp past the end
+    const int64_t q = q0 < p.ntasks ? q0 : p.ntasks - 1;
+    const double *__restrict__ vq = p.vals + q;
+    double v[SL * NCD];
+#pragma unroll
+    for (int i = 0; i < SL * NCD; ++i) v[i] = __ldg(vq + (int64_t)i * p.ntasks);    // slab 0, before the dependent chain
+    int2 t = __ldg(p.tasks + q);
+    const bool valid = q0 < p.ntasks && t.y >= 0;              // ket = -1: unused slot of a group task
+    if (t.y < 0) t.y = 0;
+    const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);   // (shell A, shell B, first A, first B)
+    digest_quartet<LA, LB, LC, LD, SL, true>(p, vq, valid, t, rb, rk, v);
 }
 
 template <int LA, int LB, int LC, int LD>

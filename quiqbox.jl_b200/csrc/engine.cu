@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <map>
+#include <atomic>
+#include <memory>
+#include <thread>
 #include <numeric>
 #include <random>
 #include <stdlib.h>
@@ -92,6 +95,17 @@ double qbx_model_flops_hrr(int la, int lb, int lc, int ld)
         for (int c = lc; c <= F - d; ++c) h += 2.0 * qbx_nc(c) * qbx_nc(d) * qbx_nc(la) * qbx_nc(lb);
     return h;
 }
+
+// QBX_TRACE=1: host-side phase times on stderr
+namespace {
+struct TraceScope {
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit TraceScope(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("QBX_TRACE") && atoi(getenv("QBX_TRACE"))) {}
+    ~TraceScope() { if (on) fprintf(stderr, "  [qbx trace] %-28s %.4f s\n", name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
+}   // namespace
 
 // ------------------------------------------------------------------ small kernels
 namespace {
@@ -312,6 +326,8 @@ Engine *Engine::create(int64_t nprim, const double *cen, const double *xpn, cons
                        const int64_t *bf_off, const int64_t *bf_prim, const double *bf_w)
 {
     (void)nprim;
+    TraceScope tr_all("create: total");
+    std::unique_ptr<TraceScope> tr(new TraceScope("create: shell reconstruction"));
     std::vector<HostShell> shells;
     struct Key {
         double c[3]; int l; std::vector<double> x;
@@ -371,6 +387,7 @@ Engine *Engine::create(int64_t nprim, const double *cen, const double *xpn, cons
     std::stable_sort(shells.begin(), shells.end(), [](const HostShell &a, const HostShell &b) {
         return a.l != b.l ? a.l < b.l : a.xpn.size() > b.xpn.size();
     });
+    tr.reset();
     return from_shells(shells, nbf, false);
 }
 
@@ -387,79 +404,93 @@ Engine *Engine::from_shells(const std::vector<HostShell> &shells, int64_t nbf, b
 static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::vector<std::pair<int, int>> sp,
                          bool sort_by_nprim, DevPairSet &out)
 {
-    struct Rec { double v[8]; };
-    std::vector<std::vector<Rec>> prims(sp.size());
+    std::unique_ptr<TraceScope> tr(new TraceScope("pairset: host"));
+    // primitive-pair records (zeta, P, K, b, 1/2zeta, 1/zeta); pairs are independent -> host threads
+    const size_t np_ = sp.size();
+    std::vector<size_t> cap(np_ + 1, 0);
+    for (size_t i = 0; i < np_; ++i) cap[i + 1] = cap[i] + sh[sp[i].first].xpn.size() * sh[sp[i].second].xpn.size();
+    // rec | prim | soa | geom live in the pinned staging area
+    std::lock_guard<std::mutex> staging_lock(qbx_staging_mutex());
+    const size_t n_rec = 8 * cap[np_], n_soa = (size_t)QBX_SOA_NF * cap[np_], n_geom = 8 * np_;
+    double *stage = (double *)qbx_staging((2 * n_rec + n_soa + n_geom + 8) * sizeof(double));
+    if (!stage) { qbx_set_error("pinned staging allocation failed"); return QBX_ERR_NOMEM; }
+    double *rec = stage, *prim = rec + n_rec, *soa = prim + n_rec, *geom = soa + n_soa;
+    std::vector<int> cnt(np_, 0);
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
-    for (size_t i = 0; i < sp.size(); ++i) {
-        const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
-        double ab2 = 0;
-        for (int d = 0; d < 3; ++d) ab2 += (A.cen[d] - B.cen[d]) * (A.cen[d] - B.cen[d]);
-        for (size_t pa = 0; pa < A.xpn.size(); ++pa)
-            for (size_t pb = 0; pb < B.xpn.size(); ++pb) {
-                const double a = A.xpn[pa], b = B.xpn[pb], z = a + b;
-                const double K = pref * A.coef[pa] * B.coef[pb] * exp(-a * b / z * ab2) / z;
-                if (fabs(K) < 1e-24) continue;
-                Rec r;
-                r.v[0] = z;
-                for (int d = 0; d < 3; ++d) r.v[1 + d] = (a * A.cen[d] + b * B.cen[d]) / z;
-                r.v[4] = K; r.v[5] = b; r.v[6] = 0.5 / z; r.v[7] = 1.0 / z;
-                prims[i].push_back(r);
-            }
-    }
-    std::vector<int> order(sp.size());
+    qbx_parallel_for(np_, 256, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
+            double ab2 = 0;
+            for (int d = 0; d < 3; ++d) ab2 += (A.cen[d] - B.cen[d]) * (A.cen[d] - B.cen[d]);
+            double *r = rec + 8 * cap[i];
+            int c = 0;
+            for (size_t pa = 0; pa < A.xpn.size(); ++pa)
+                for (size_t pb = 0; pb < B.xpn.size(); ++pb) {
+                    const double a = A.xpn[pa], b = B.xpn[pb], z = a + b;
+                    const double K = pref * A.coef[pa] * B.coef[pb] * exp(-a * b / z * ab2) / z;
+                    if (fabs(K) < 1e-24) continue;
+                    double *v = r + 8 * c++;
+                    v[0] = z;
+                    for (int d = 0; d < 3; ++d) v[1 + d] = (a * A.cen[d] + b * B.cen[d]) / z;
+                    v[4] = K; v[5] = b; v[6] = 0.5 / z; v[7] = 1.0 / z;
+                }
+            cnt[i] = c;
+        }
+    });
+    std::vector<int> order(np_);
     std::iota(order.begin(), order.end(), 0);
     if (sort_by_nprim)
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prims[x].size() > prims[y].size(); });
-    std::vector<int2> shells(sp.size());
-    std::vector<int> poff(sp.size() + 1, 0);
-    std::vector<double> geom(8 * sp.size(), 0.0), prim;
-    out.h_nprim.resize(sp.size());
-    for (size_t n = 0; n < sp.size(); ++n) {
-        const int i = order[n];
-        const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
-        shells[n] = make_int2(sp[i].first, sp[i].second);
-        for (int d = 0; d < 3; ++d) { geom[8 * n + d] = A.cen[d]; geom[8 * n + 3 + d] = A.cen[d] - B.cen[d]; }
-        for (auto &r : prims[i]) prim.insert(prim.end(), r.v, r.v + 8);
-        poff[n + 1] = poff[n] + (int)prims[i].size();
-        out.h_nprim[n] = (int)prims[i].size();
-    }
-    // transposed copy for coalesced ket-side loads (see PairSet in eri_class.cuh)
-    std::vector<double> soa((size_t)QBX_SOA_NF * poff.back(), 0.0);
-    std::vector<int2> soa_idx(sp.size());
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+    std::vector<int2> shells(np_);
+    std::vector<int> poff(np_ + 1, 0);
+    out.h_nprim.resize(np_);
+    for (size_t n = 0; n < np_; ++n) { out.h_nprim[n] = cnt[order[n]]; poff[n + 1] = poff[n] + cnt[order[n]]; }
+    const size_t n_prim = 8 * (size_t)poff[np_], n_soa_used = (size_t)QBX_SOA_NF * poff[np_];
+    // transposed copy for coalesced ket-side loads (see PairSet in eri_class.cuh): runs of pairs with
+    // the same primitive count form one block [primitive][field][pair]
+    std::vector<int2> soa_idx(np_);
     {
         size_t base = 0, g0 = 0;
-        while (g0 < sp.size()) {
+        while (g0 < np_) {
             size_t g1 = g0;
-            while (g1 < sp.size() && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
-            const size_t g = g1 - g0, np = (size_t)out.h_nprim[g0];
-            for (size_t j = g0; j < g1; ++j) {
-                soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
-                for (size_t pp = 0; pp < np; ++pp) {
-                    const double *r = prim.data() + 8 * ((size_t)poff[j] + pp);
-                    const double f[QBX_SOA_NF] = {r[0], r[1], r[2], r[3], r[4], r[5], r[6]};
-                    for (int k = 0; k < QBX_SOA_NF; ++k) soa[base + (pp * QBX_SOA_NF + k) * g + (j - g0)] = f[k];
-                }
-            }
-            base += g * np * QBX_SOA_NF;
+            while (g1 < np_ && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
+            const size_t g = g1 - g0;
+            for (size_t j = g0; j < g1; ++j) soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
+            base += g * (size_t)out.h_nprim[g0] * QBX_SOA_NF;
             g0 = g1;
         }
     }
+    qbx_parallel_for(np_, 256, [&](size_t lo, size_t hi) {
+        for (size_t n = lo; n < hi; ++n) {
+            const int i = order[n];
+            const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
+            shells[n] = make_int2(sp[i].first, sp[i].second);
+            for (int d = 0; d < 3; ++d) { geom[8 * n + d] = A.cen[d]; geom[8 * n + 3 + d] = A.cen[d] - B.cen[d]; }
+            geom[8 * n + 6] = geom[8 * n + 7] = 0.0;
+            const double *r = rec + 8 * cap[i];
+            std::copy(r, r + 8 * (size_t)cnt[i], prim + 8 * (size_t)poff[n]);
+            const size_t b0 = (size_t)soa_idx[n].x, g = (size_t)soa_idx[n].y;
+            for (int pp = 0; pp < cnt[i]; ++pp)
+                for (int k = 0; k < QBX_SOA_NF; ++k) soa[b0 + ((size_t)pp * QBX_SOA_NF + k) * g] = r[8 * pp + k];
+        }
+    });
     out.la = la; out.lb = lb; out.npair = (int)sp.size(); out.nprim = poff.back();
-    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
+    tr.reset(new TraceScope("pairset: upload"));
+    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa_used) * sizeof(double)));
     QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, soa_idx.size()) * sizeof(int2)));
-    if (!soa.empty()) QBX_CUDA(cudaMemcpy(out.soa, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
-    if (!soa_idx.empty()) QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), soa_idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
     QBX_CUDA(qbx_dmalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
     QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
-    QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, geom.size()) * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, prim.size()) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, n_geom) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, n_prim) * sizeof(double)));
     QBX_CUDA(qbx_dmalloc(&out.schwarz, std::max<size_t>(1, sp.size()) * sizeof(double)));
+    if (n_soa_used) QBX_CUDA(cudaMemcpy(out.soa, soa, n_soa_used * sizeof(double), cudaMemcpyHostToDevice));
+    if (!soa_idx.empty()) QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), soa_idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
     if (!sp.empty()) {
         QBX_CUDA(cudaMemcpy(out.shells, shells.data(), shells.size() * sizeof(int2), cudaMemcpyHostToDevice));
-        QBX_CUDA(cudaMemcpy(out.geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice));
+        QBX_CUDA(cudaMemcpy(out.geom, geom, n_geom * sizeof(double), cudaMemcpyHostToDevice));
     }
     QBX_CUDA(cudaMemcpy(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if (!prim.empty()) QBX_CUDA(cudaMemcpy(out.prim, prim.data(), prim.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_prim) QBX_CUDA(cudaMemcpy(out.prim, prim, n_prim * sizeof(double), cudaMemcpyHostToDevice));
     return QBX_OK;
 }
 
@@ -512,6 +543,7 @@ int Engine::upload(bool pair_adjacent)
             if (P.npair) QBX_CUDA(cudaMemcpy(P.info, info.data(), info.size() * sizeof(int4), cudaMemcpyHostToDevice));
             // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
             if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
+                TraceScope trg("group build");
                 if ((rc = qbx_group_build(shells_, sh, groups_))) return rc;
                 use_groups_ = groups_.ng > 0 && groups_.ng < P.npair;     // only when something is shared
             }
@@ -602,22 +634,28 @@ int Engine::run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, c
 int Engine::ensure_schwarz(cudaStream_t s)
 {
     if (have_schwarz_) return QBX_OK;
+    // the six diagonal classes (ab|ab) are independent: side streams, nothing waits on the host
+    int rc = fork(s);
+    if (rc) return rc;
+    std::vector<void *> scratch;
+    int k = 0;
     for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
         DevPairSet &P = pairs_[pc];
         if (P.npair == 0) continue;
         const ClassOps *ops = qbx_class_ops(pc, pc);
+        cudaStream_t cs = side_[k++ % kSide];
         int2 *t = nullptr; double *v = nullptr;
         QBX_CUDA(qbx_dmalloc(&t, P.npair * sizeof(int2)));
         QBX_CUDA(qbx_dmalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
-        k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, s>>>(P.npair, t);
-        int rc = run_eri(pc, pc, t, P.npair, v, s);
-        if (rc) return rc;
+        scratch.push_back(t); scratch.push_back(v);
+        k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, cs>>>(P.npair, t);
+        if ((rc = run_eri(pc, pc, t, P.npair, v, cs))) return rc;
         const int nab = qbx_nc(P.la) * qbx_nc(P.lb);
-        k_schwarz<<<(P.npair + 127) / 128, 128, 0, s>>>(v, P.npair, nab, P.schwarz);
+        k_schwarz<<<(P.npair + 127) / 128, 128, 0, cs>>>(v, P.npair, nab, P.schwarz);
         QBX_CUDA(cudaGetLastError());
-        QBX_CUDA(cudaStreamSynchronize(s));
-        qbx_pool_free(t); qbx_pool_free(v);
     }
+    if ((rc = join(s))) return rc;
+    for (void *p : scratch) qbx_pool_free_async(p);          // after the join: later users are ordered behind it
     have_schwarz_ = true;
     return QBX_OK;
 }

@@ -31,61 +31,84 @@ __device__ __forceinline__ bool member_ok(int j, int i, int same, double qi, con
     return j >= 0 && (!same || j <= i) && qi * Qk[j] >= tol;
 }
 
+// The three task-building kernels give one WARP to a bra row: lanes take groups g = lane, lane+32, ..
+// and positions inside the row come from ballots / a shuffle scan, in group order.
+__device__ __forceinline__ bool group_any(const int *members, int g, int i, int same, double qi, const double *Qk, double tol)
+{
+    bool any = false;
+#pragma unroll
+    for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
+    return any;
+}
+
 __global__ void k_gcount(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
                          int *cnt)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (i >= nb) return;
     const double qi = Qb[i];
     int c = 0;
-    for (int g = 0; g < ng; ++g) {
-        bool any = false;
-        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
-        c += any;
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+        const int g = g0 + lane;
+        const bool any = g < ng && group_any(members, g, i, same, qi, Qk, tol);
+        c += __popc(__ballot_sync(0xffffffffu, any));
     }
-    cnt[i] = c;
+    if (lane == 0) cnt[i] = c;
 }
 
 __global__ void k_gcount_owned(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
                                const int *nmem, const int64_t *growoff, int rank, int nranks, int *cnt_tasks, int *cnt_slots)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (i >= nb) return;
     const double qi = Qb[i];
     int64_t idx = growoff[i];
     int ct = 0, cs = 0;
-    for (int g = 0; g < ng; ++g) {
-        bool any = false;
-        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
-        if (!any) continue;
-        if ((idx / QBX_GRP_CHUNK) % nranks == rank) { ++ct; cs += nmem[g]; }
-        ++idx;
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+        const int g = g0 + lane;
+        const bool any = g < ng && group_any(members, g, i, same, qi, Qk, tol);
+        const unsigned mask = __ballot_sync(0xffffffffu, any);
+        if (any) {
+            const int64_t my = idx + __popc(mask & ((1u << lane) - 1u));
+            if ((my / QBX_GRP_CHUNK) % nranks == rank) { ++ct; cs += nmem[g]; }
+        }
+        idx += __popc(mask);
     }
-    cnt_tasks[i] = ct;
-    cnt_slots[i] = cs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ct += __shfl_xor_sync(0xffffffffu, ct, o); cs += __shfl_xor_sync(0xffffffffu, cs, o); }
+    if (lane == 0) { cnt_tasks[i] = ct; cnt_slots[i] = cs; }
 }
 
 __global__ void k_gfill(const double *Qb, const double *Qk, int nb, int same, double tol, int ng, const int *members,
                         const int *nmem, const int64_t *growoff, int rank, int nranks, const int64_t *toff,
                         const int64_t *soff, int *gt_bra, int *gt_grp, int *gt_off, int2 *tasks)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (i >= nb) return;
     const double qi = Qb[i];
     int64_t idx = growoff[i], t = toff[i], s = soff[i];
-    for (int g = 0; g < ng; ++g) {
-        bool any = false;
-        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) any |= member_ok(members[g * QBX_GRP_MAXMEM + m], i, same, qi, Qk, tol);
-        if (!any) continue;
-        if ((idx / QBX_GRP_CHUNK) % nranks == rank) {
-            gt_bra[t] = i; gt_grp[t] = g; gt_off[t] = (int)s;
-            for (int m = 0; m < nmem[g]; ++m) {
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+        const int g = g0 + lane;
+        const bool any = g < ng && group_any(members, g, i, same, qi, Qk, tol);
+        const unsigned mask = __ballot_sync(0xffffffffu, any);
+        const int64_t my = idx + __popc(mask & ((1u << lane) - 1u));
+        const bool own = any && (my / QBX_GRP_CHUNK) % nranks == rank;
+        const unsigned omask = __ballot_sync(0xffffffffu, own);
+        const int nm = own ? nmem[g] : 0;
+        int incl = nm;                                        // inclusive scan of the slot counts of the owned lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (own) {
+            const int64_t tt = t + __popc(omask & ((1u << lane) - 1u)), ss = s + incl - nm;
+            gt_bra[tt] = i; gt_grp[tt] = g; gt_off[tt] = (int)ss;
+            for (int m = 0; m < nm; ++m) {
                 const int j = members[g * QBX_GRP_MAXMEM + m];
-                tasks[s + m] = make_int2(i, member_ok(j, i, same, qi, Qk, tol) ? j : -1);
+                tasks[ss + m] = make_int2(i, member_ok(j, i, same, qi, Qk, tol) ? j : -1);
             }
-            ++t; s += nmem[g];
         }
-        ++idx;
+        idx += __popc(mask);
+        t += __popc(omask);
+        s += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -298,7 +321,8 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
     struct Rec { double v[QBX_GRP_NF]; };
     std::vector<std::vector<Rec>> prims(ng0);
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
-    for (size_t g = 0; g < ng0; ++g) {
+    qbx_parallel_for(ng0, 32, [&](size_t lo, size_t hi) {
+    for (size_t g = lo; g < hi; ++g) {
         const PG &P = pgs[gp_pq[g].first], &Q = pgs[gp_pq[g].second];
         double pq2 = 0;
         for (int d = 0; d < 3; ++d) pq2 += (P.cen[d] - Q.cen[d]) * (P.cen[d] - Q.cen[d]);
@@ -325,6 +349,7 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
                 prims[g].push_back(r);
             }
     }
+    });
     // 4. order groups by primitive count (descending, stable) and upload
     std::vector<int> order(ng0);
     for (size_t g = 0; g < ng0; ++g) order[g] = (int)g;
@@ -380,7 +405,7 @@ int qbx_group_count(const GroupSet &G, const DevPairSet &B, const DevPairSet &K,
                     TaskScratch &ts, int64_t *d_total, cudaStream_t s)
 {
     if (B.npair == 0 || G.ng == 0) return QBX_OK;
-    const int nb = B.npair, grid = (nb + 127) / 128;
+    const int nb = B.npair, grid = (int)(((int64_t)nb * 32 + 127) / 128);
     for (int i = 0; i < 3; ++i) {
         QBX_CUDA(qbx_dmalloc(&ts.cnt[i], nb * sizeof(int)));
         QBX_CUDA(qbx_dmalloc(&ts.off[i], (nb + 1) * sizeof(int64_t)));
@@ -400,7 +425,7 @@ int qbx_group_fill(const GroupSet &G, const DevPairSet &B, const DevPairSet &K, 
 {
     tl = TaskList();
     if (B.npair == 0 || G.ng == 0) return QBX_OK;
-    const int nb = B.npair, grid = (nb + 127) / 128;
+    const int nb = B.npair, grid = (int)(((int64_t)nb * 32 + 127) / 128);
     tl.ngt = (int)h_total[1];
     tl.n = h_total[2];
     if (tl.ngt <= 0) { tl.ngt = 0; tl.n = 0; return QBX_OK; }

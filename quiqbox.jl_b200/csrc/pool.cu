@@ -122,3 +122,24 @@ void qbx_pool_counts(int64_t *hits, int64_t *misses, int64_t *idle_bytes)
     std::lock_guard<std::mutex> lk(g_pool.mu);
     *hits = g_pool.hits; *misses = g_pool.misses; *idle_bytes = (int64_t)g_pool.idle_bytes;
 }
+
+// Pinned staging area for the host-built tables of a basis (primitive-pair records): resident pages
+// (no first-touch faults on every qbx_basis_create) and DMA-able without a bounce buffer.
+// Grow-only; the caller holds qbx_staging_mutex() while it uses the pointer.
+std::mutex &qbx_staging_mutex()
+{
+    static std::mutex mu;
+    return mu;
+}
+
+void *qbx_staging(size_t bytes)
+{
+    static void *buf = nullptr;
+    static size_t cap = 0;
+    if (bytes > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = bytes + bytes / 2;
+        if (cudaMallocHost(&buf, cap) != cudaSuccess) { cudaGetLastError(); buf = nullptr; cap = 0; }
+    }
+    return buf;
+}

@@ -2,7 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qbx.h"
@@ -31,9 +35,31 @@ cudaError_t qbx_pool_malloc(void **p, size_t bytes);
 cudaError_t qbx_pool_free(void *p);
 cudaError_t qbx_pool_free_async(void *p);
 void *qbx_pinned(size_t bytes);
+void *qbx_staging(size_t bytes);
+std::mutex &qbx_staging_mutex();
 void qbx_pool_release();
 void qbx_pool_counts(int64_t *hits, int64_t *misses, int64_t *idle_bytes);
 template <class T> inline cudaError_t qbx_dmalloc(T **p, size_t bytes) { return qbx_pool_malloc((void **)p, bytes); }
+
+// f(lo, hi) over [0, n) on a few host threads, `grain` items at a time
+template <class F>
+inline void qbx_parallel_for(size_t n, size_t grain, F f)
+{
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), (n + grain - 1) / grain);
+    if (nt <= 1) { f(0, n); return; }
+    std::atomic<size_t> next(0);
+    auto work = [&] {
+        for (;;) {
+            const size_t lo = next.fetch_add(grain);
+            if (lo >= n) return;
+            f(lo, std::min(n, lo + grain));
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
 
 __host__ __device__ constexpr int qbx_nc(int l) { return (l + 1) * (l + 2) / 2; }
 

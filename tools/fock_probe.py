@@ -1,0 +1,33 @@
+"""Time the stored-mode Fock build (digestion kernels) of a water cluster: ms per build, CUDA events."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np, torch
+import quiqbox_b200 as qb
+from quiqbox_b200 import lib as L
+from molecules import water_cluster
+nw = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+nuc, xyz = water_cluster(nw)
+bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+mod = qb.MultiOrbitalData.from_orbitals(bs)
+arrs = [np.ascontiguousarray(a) for a in (mod.cen, mod.xpn, mod.ang, mod.bf_off, mod.bf_prim, mod.bf_w)]
+n = mod.nbf
+D = np.random.RandomState(0).uniform(-1, 1, (n, n)); D = (D + D.T) / (2 * n)
+L.init(); lib = L.load()
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+L.check(lib.qbx_set_stream(C.c_void_p(stream.cuda_stream)))
+h = C.c_void_p()
+L.check(lib.qbx_basis_create(mod.nprim, L.ptr(arrs[0]), L.ptr(arrs[1]), L.ptr(arrs[2]), mod.nbf, L.ptr(arrs[3]), L.ptr(arrs[4]), L.ptr(arrs[5]), C.byref(h)))
+L.check(lib.qbx_eri_store(h, 1e-12, 0, 0, 1))
+dDJ = torch.tensor(2 * D, device="cuda").contiguous(); dDK = torch.tensor(D, device="cuda").contiguous()
+dG = torch.zeros(n * n, dtype=torch.float64, device="cuda")
+def fock():
+    L.check(lib.qbx_fock_build_device(h, 1, C.c_void_p(dDJ.data_ptr()), C.c_void_p(dDK.data_ptr()), C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))
+for _ in range(3): fock()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+torch.cuda.synchronize(); ev[0].record(stream)
+for _ in range(reps): fock()
+ev[1].record(stream); torch.cuda.synchronize()
+print("fock build: %.3f ms   checksum %.12e" % (ev[0].elapsed_time(ev[1]) / reps, float(dG.double().abs().sum())))
+lib.qbx_basis_destroy(h)
