@@ -12,11 +12,14 @@ One *step* = one pass of the hot path over the whole shard:
         for N > 1, the NCCL all-reduce of the partial G matrices.
 `value` = unique contracted ERIs of the whole job / step time (contracted ERIs/s); the Fock
 build alone (stored mode, the per-SCF-iteration cost) is reported as `fock_build_ms`.
-Inputs are resident in HBM; the packed store (25.7 GB at N = 1) is far larger than L2.
+Inputs are resident in HBM; the packed store (10.7 GB at N = 1 with the default 1e-12 Schwarz
+screening, 25.7 GB unscreened) is far larger than L2.
 
 `e2e` = the same metric through the C ABI with HOST buffers, every step: qbx_basis_create
 (basis H2D) -> qbx_eri_store (Schwarz bounds, task lists, all ERIs) -> qbx_fock_build
-(densities H2D, G D2H) -> qbx_basis_destroy.
+(densities H2D, G D2H) -> qbx_basis_destroy.  Nothing is carried over between steps except
+freed device blocks in the library's allocation pool (qbx.h: qbx_pool_trim); one untimed
+warm-up step, then the median of three.
 
 `--impl reference` times the CPU restatement of the reference's algorithm (oracle/) on the
 host cores on a bounded sample of the same workload's unique contracted ERIs.
@@ -301,7 +304,10 @@ def main():
         t = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pool = np.zeros(3, dtype=np.int64)
+        L.check(lib.qbx_pool_trim(L.ptr(pool)))
         e2e = {"value": tot_values / t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "pool": {"reused_blocks": int(pool[0]), "driver_allocations": int(pool[1]), "idle_bytes": int(pool[2])},
                "d2h_bytes_per_step": int(Gh.nbytes), "seconds_per_step": t.item(),
                "phase_seconds_rank0": {"qbx_basis_create": phases[0], "qbx_eri_store": phases[1], "qbx_fock_build": phases[2]},
                "path": "qbx_basis_create -> qbx_eri_store(stored) -> qbx_fock_build (host D, host G) -> qbx_basis_destroy"}

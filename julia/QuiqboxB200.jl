@@ -28,6 +28,9 @@ function __init__()
     check(ccall((:qbx_init, libqbx), Cint, (Cint, Ptr{Cint}), parse(Cint, get(ENV, "LOCAL_RANK", "0")), ndev))
 end
 
+"Return the library's idle device blocks to the driver (they are kept for the next basis otherwise)."
+trim_pool() = check(ccall((:qbx_pool_trim, libqbx), Cint, (Ptr{Int64},), C_NULL))
+
 # ---- opaque handle: owns the device copy of one basis set -----------------------------------
 mutable struct DeviceBasis
     ptr::Ptr{Cvoid}

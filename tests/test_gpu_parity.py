@@ -408,3 +408,34 @@ def test_irregular_basis_falls_back_to_generic_kernels():
     dm = qb.DeviceBasis(mixed)
     assert dm.info()["class_path"] == 0
     assert np.max(np.abs(qb.elecRepulsions(dm) - oracle.OracleBasis(mixed).eri_tensor())) < 1e-12
+
+
+def test_allocation_pool_reuse_and_trim():
+    """A geometry scan creates, stores and destroys one basis per point (HartreeFock.jl:583-606 runs once per
+    geometry).  The library's device blocks are recycled between the points (qbx.h: qbx_pool_trim); the
+    results must not depend on whether a block is fresh or recycled, and a trim hands everything back."""
+    from quiqbox_b200 import lib as L
+    lib = L.load()
+    L.check(lib.qbx_pool_trim(None))
+    bs = mol_basis(*h2o(), "cc-pVDZ")
+    n = len(bs)
+    DJ, DK = _rand_sym(n, 71), _rand_sym(n, 72)
+    Gs = []
+    for _ in range(3):
+        db = qb.DeviceBasis(bs)
+        Gs.append(qb.DeviceERI(db, mode="stored", screen_tol=1e-12).getGcore(DJ, [DK])[0])
+        db.close()                                             # qbx_basis_destroy: blocks go back to the pool
+    assert np.array_equal(Gs[0], Gs[1]) or np.max(np.abs(Gs[0] - Gs[1])) < 1e-13   # atomics: summation order only
+    assert np.max(np.abs(Gs[0] - Gs[2])) < 1e-13
+    counts = np.zeros(3, dtype=np.int64)
+    L.check(lib.qbx_pool_trim(L.ptr(counts)))
+    assert counts[0] > 0 and counts[1] > 0                     # blocks were reused, and some came from the driver
+    L.check(lib.qbx_pool_trim(L.ptr(counts)))
+    assert counts[2] == 0                                      # nothing idle after a trim
+    # a different geometry right after a trim: fresh blocks, still correct against the oracle
+    nuc, xyz = h2o()
+    xyz2 = [np.asarray(c, dtype=float) * 1.05 for c in xyz]
+    bs2 = mol_basis(nuc, xyz2, "6-31G")
+    T = qb.elecRepulsions(bs2)
+    Tref = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs2)).eri_tensor()
+    assert np.max(np.abs(T - Tref)) < 1e-12
