@@ -35,21 +35,44 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Segmented warp reduction: a segment is a run of consecutive lanes that update the same address
+// (same bra pair, or same bra pair and same shell C); `end` is the last lane of the caller's run.
+// After the five steps the FIRST lane of every run holds the run's sum.  A warp that sits inside
+// one run (the common case) does exactly the work of a butterfly sum; a warp that straddles two or
+// three runs -- every other warp on a screened list, where a (bra pair, C) run is some tens of kets
+// long, and every warp of the general-contraction classes -- still issues one RED per run instead
+// of one per lane (ncu, profiles/r01: the kernels are bound by the L2 RED request rate).
+__device__ __forceinline__ double seg_sum(double v, int end, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o <= end) v += y;
+    }
+    return v;
+}
+
+// runs of equal keys over the lanes: first-lane flag and last lane of the caller's run
+__device__ __forceinline__ void seg_runs(int key0, int key1, int lane, bool &head, int &end)
+{
+    const int p0 = __shfl_up_sync(0xffffffffu, key0, 1), p1 = __shfl_up_sync(0xffffffffu, key1, 1);
+    head = lane == 0 || p0 != key0 || p1 != key1;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+    end = above ? __ffs(above) - 2 : 31;
+}
+
 // K updates of one bra-side function x (= a or b) against the ket functions: K[x c] is one address
-// per warp when the warp shares C (shuffle reduction, one RED), K[x d] is consecutive over the lanes.
+// per run of lanes that share the bra pair and C (segmented shuffle reduction, one RED per run),
+// K[x d] is consecutive over the lanes.
 template <int NCc, int ND>
 __device__ __forceinline__ void digest_flush_row(double *Kt, int N, int ix, int ic, int id, const double *kxc,
-                                                 const double *kxd, double f, bool uniC, bool valid, bool lane0)
+                                                 const double *kxd, double f, bool headC, int endC, bool valid, int lane)
 {
 #pragma unroll
     for (int c = 0; c < NCc; ++c) {
-        double x = f * kxc[c];
-        if (uniC) {
-            x = warp_sum(x);
-            if (lane0) atomicAdd(Kt + (ic + c) + N * ix, x);
-        } else if (valid) {
-            atomicAdd(Kt + (ic + c) + N * ix, x);
-        }
+        const double x = seg_sum(f * kxc[c], endC, lane);
+        if (headC && x != 0.0) atomicAdd(Kt + (ic + c) + N * ix, x);
     }
     if (valid) {
 #pragma unroll
@@ -89,9 +112,11 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
     if (rb.x == rb.y) f *= 0.5;
     if (rk.x == rk.y) f *= 0.5;
     if (p.same_class && t.x == t.y) f *= 0.5;
-    const bool uniAB = __all_sync(0xffffffffu, t.x == __shfl_sync(0xffffffffu, t.x, 0));
-    const bool uniC = uniAB && __all_sync(0xffffffffu, rk.x == __shfl_sync(0xffffffffu, rk.x, 0));
-    const bool lane0 = (threadIdx.x & 31) == 0;
+    const int lane = threadIdx.x & 31;
+    bool headAB, headC;
+    int endAB, endC;
+    seg_runs(t.x, 0, lane, headAB, endAB);                   // runs of one bra pair: J[ab]
+    seg_runs(t.x, rk.x, lane, headC, endC);                  // runs of one bra pair and one shell C: K[ac], K[bc]
     const int N = p.nbf;                                      // internal dimension
     const int ia = rb.z, ib = rb.w, ic = rk.z, id = rk.w;
     const double *__restrict__ DJ = p.DJ;
@@ -156,22 +181,17 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
                         kbd[ob * ND + d] = fma(dac[c], x, kbd[ob * ND + d]);
                     }
                 if (coul) {                                   // J[ab]: one address per warp
-                    j *= 2.0 * f;
-                    if (uniAB) {
-                        j = warp_sum(j);
-                        if (lane0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
-                    } else if (valid) {
-                        atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
-                    }
+                    j = seg_sum(j * 2.0 * f, endAB, lane);
+                    if (headAB && j != 0.0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
                 }
-                if (!KEEP_B) digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc, kbd, f, uniC, valid, lane0);
+                if (!KEEP_B) digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc, kbd, f, headC, endC, valid, lane);
             }
-            digest_flush_row<NCc, ND>(Kt, N, ia + a, ic, id, kac, kad, f, uniC, valid, lane0);
+            digest_flush_row<NCc, ND>(Kt, N, ia + a, ic, id, kac, kad, f, headC, endC, valid, lane);
         }
         if (KEEP_B) {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
-                digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc + b * NCc, kbd + b * ND, f, uniC, valid, lane0);
+                digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc + b * NCc, kbd + b * ND, f, headC, endC, valid, lane);
         }
         if (coul && valid) {                                  // J[cd]: consecutive over the lanes
 #pragma unroll

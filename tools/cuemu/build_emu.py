@@ -18,7 +18,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "quiqbox.jl_b200", "csrc")
-OUT = os.path.join(HERE, "_build")
+SAN = os.environ.get("QBX_EMU_SANITIZE", "")           # e.g. "address,undefined": a separate build directory
+OUT = os.path.join(HERE, "_build" + ("_san" if SAN else ""))
 SRC = os.path.join(OUT, "src")
 LIB = os.path.join(OUT, "libqbx_emu.so")
 CXX = os.environ.get("CXX", "g++")
@@ -27,6 +28,8 @@ FLAGS = ["-std=c++17", "-O1", "-g0", "-fPIC", "-pthread", "-Wno-unknown-pragmas"
 
 CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
+if SAN:
+    FLAGS = [f for f in FLAGS if f not in ("-O1", "-g0")] + ["-O1", "-g", "-fno-omit-frame-pointer", f"-fsanitize={SAN}"]
 UNITS = ["api", "generic", "engine", "eri_coop", "eri_group", "pool"]
 
 _launch = re.compile(r"([A-Za-z_]\w*(?:\s*<[^<>;(){}]*>)?)\s*<<<")
@@ -147,7 +150,7 @@ def build(jobs=None, force=False, verbose=False):
                 if rc != 0:
                     raise RuntimeError(f"{CXX} failed for {obj}:\n{out[-6000:]}")
     if work or not os.path.exists(LIB):
-        r = subprocess.run([CXX, "-shared", "-pthread", "-o", LIB] + objs, capture_output=True, text=True)
+        r = subprocess.run([CXX, "-shared", "-pthread", "-o", LIB] + ([f"-fsanitize={SAN}"] if SAN else []) + objs, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
         if verbose:

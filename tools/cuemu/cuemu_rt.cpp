@@ -8,6 +8,10 @@
 #include <mutex>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
+
 #if !defined(__x86_64__)
 #error "cuemu's context switch is written for x86-64"
 #endif
@@ -105,6 +109,10 @@ static void trampoline()
 static void prepare(Thread &t, size_t idx)
 {
     char *top = g_stacks + (idx + 1) * STACK_BYTES;
+#if defined(__SANITIZE_ADDRESS__)
+    // frames of device threads that ended inside the trampoline were never unwound
+    __asan_unpoison_memory_region(g_stacks + idx * STACK_BYTES, STACK_BYTES);
+#endif
     void **sp = (void **)top;
     *--sp = nullptr;                            // fake return address of trampoline (keeps the ABI alignment)
     *--sp = (void *)&trampoline;

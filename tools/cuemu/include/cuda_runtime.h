@@ -45,9 +45,9 @@ struct dim3 {
     unsigned x, y, z;
     constexpr dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct int2 { int x, y; };
-struct int4 { int x, y, z, w; };
-struct float2 { float x, y; };
+struct alignas(8) int2 { int x, y; };          // CUDA's alignments: a misaligned vector access is
+struct alignas(16) int4 { int x, y, z, w; };   // an error on the GPU; UBSan reports it here
+struct alignas(8) float2 { float x, y; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
