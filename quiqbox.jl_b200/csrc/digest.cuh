@@ -53,11 +53,14 @@ __device__ __forceinline__ double seg_sum(double v, int end, int lane)
 }
 
 // runs of equal keys over the lanes: first-lane flag and last lane of the caller's run
-__device__ __forceinline__ void seg_runs(int key0, int key1, int lane, bool &head, int &end)
+// (seg = 0, the A/B switch QBX_DIGEST_SEG=0: a warp that is not one single run treats every lane
+//  as a run of its own, i.e. the first version's per-lane REDs)
+__device__ __forceinline__ void seg_runs(int key0, int key1, int lane, int seg, bool &head, int &end)
 {
     const int p0 = __shfl_up_sync(0xffffffffu, key0, 1), p1 = __shfl_up_sync(0xffffffffu, key1, 1);
     head = lane == 0 || p0 != key0 || p1 != key1;
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (!seg && heads != 1u) { head = true; heads = 0xffffffffu; }
     const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
     end = above ? __ffs(above) - 2 : 31;
 }
@@ -115,8 +118,8 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
     const int lane = threadIdx.x & 31;
     bool headAB, headC;
     int endAB, endC;
-    seg_runs(t.x, 0, lane, headAB, endAB);                   // runs of one bra pair: J[ab]
-    seg_runs(t.x, rk.x, lane, headC, endC);                  // runs of one bra pair and one shell C: K[ac], K[bc]
+    seg_runs(t.x, 0, lane, p.seg, headAB, endAB);                   // runs of one bra pair: J[ab]
+    seg_runs(t.x, rk.x, lane, p.seg, headC, endC);                  // runs of one bra pair and one shell C: K[ac], K[bc]
     const int N = p.nbf;                                      // internal dimension
     const int ia = rb.z, ib = rb.w, ic = rk.z, id = rk.w;
     const double *__restrict__ DJ = p.DJ;

@@ -964,6 +964,8 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             a.bra_info = pairs_[bc].info; a.ket_info = pairs_[kc].info;
             static const int spread = getenv("QBX_DIGEST_SPREAD") ? atoi(getenv("QBX_DIGEST_SPREAD")) : QBX_DIGEST_SPREAD;
             a.spread = spread > 0 ? spread : 1;
+            static const int seg = getenv("QBX_DIGEST_SEG") ? atoi(getenv("QBX_DIGEST_SEG")) : 1;
+            a.seg = seg;
             a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {

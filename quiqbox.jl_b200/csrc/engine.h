@@ -25,6 +25,7 @@ struct DigestArgs {
     const double *vals;          // [ncomp][ntasks]
     int nbf, nmat, same_class;   // nbf = internal dimension here
     int spread;                  // number of block slots the task list is dealt over (see digest.cuh)
+    int seg;                     // 1: segmented warp reductions (default); 0: per-lane REDs when a warp is not uniform (QBX_DIGEST_SEG, A/B switch)
     const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
 };

@@ -223,31 +223,33 @@ struct CoopArgs {
     int L, buf, acc_off, acc_n, y_off, ncomp, NA, NB, NCc, ND;
     int nvrr, nxfer, nhrr;
     Level vrr[9], xfer[5], hrr[4], acc;
+    double boys_inv[QBX_BOYS_DEG];     // 1 / (2 (L + k) + 1)
 };
 
-__device__ __forceinline__ void boys_rt(const BoysTable &tb, double T, double scale, int L, double *F)
+// Boys function with a run-time order: same evaluator as boys_eval<L> (boys.cuh) -- two table
+// loads, the Taylor coefficients by downward recursion at the table point -- with the
+// reciprocals 1/(2(L+k)+1) passed in (kernel parameters, constant bank).
+__device__ __forceinline__ void boys_rt(const BoysTable &tb, const double *inv_odd, double T, double scale, int L, double *F)
 {
     const bool big = T >= QBX_BOYS_TMAX;
     const int i = big ? (QBX_BOYS_NROW - 2) : __double2int_rn(T * QBX_BOYS_STEP_INV);
-    const double *row = tb.f + i * QBX_BOYS_NCOL + L;
-    const double mx = fma((double)i, 1.0 / QBX_BOYS_STEP_INV, -T);
-    double r = __ldg(row + 7);
-    r = fma(r, mx * (1.0 / 7.0), __ldg(row + 6));
-    r = fma(r, mx * (1.0 / 6.0), __ldg(row + 5));
-    r = fma(r, mx * (1.0 / 5.0), __ldg(row + 4));
-    r = fma(r, mx * (1.0 / 4.0), __ldg(row + 3));
-    r = fma(r, mx * (1.0 / 3.0), __ldg(row + 2));
-    r = fma(r, mx * (1.0 / 2.0), __ldg(row + 1));
-    r = fma(r, mx, __ldg(row));
-    double ex = 1.0 / 5040.0;
-    ex = fma(ex, mx, 1.0 / 720.0);
+    const double ctop = __ldg(tb.f + i * QBX_BOYS_NCOL + L + QBX_BOYS_DEG), ei = __ldg(tb.e + i);
+    const double Ti = (double)i * (1.0 / QBX_BOYS_STEP_INV), mx = Ti - T, t2i = 2.0 * Ti;
+    double c[QBX_BOYS_DEG + 1];
+    c[QBX_BOYS_DEG] = ctop;
+#pragma unroll
+    for (int k = QBX_BOYS_DEG - 1; k >= 0; --k) c[k] = fma(t2i, c[k + 1], ei) * inv_odd[k];
+    double r = ctop;
+#pragma unroll
+    for (int k = QBX_BOYS_DEG - 1; k >= 0; --k) r = fma(r, mx * (1.0 / (k + 1.0)), c[k]);
+    double ex = 1.0 / 720.0;
     ex = fma(ex, mx, 1.0 / 120.0);
     ex = fma(ex, mx, 1.0 / 24.0);
     ex = fma(ex, mx, 1.0 / 6.0);
     ex = fma(ex, mx, 0.5);
     ex = fma(ex, mx, 1.0);
     ex = fma(ex, mx, 1.0);
-    ex *= __ldg(tb.e + i);
+    ex *= ei;
     const double rt = rsqrt(T), h = 0.5 * rt * rt;
     double as = 0.88622692545275801365 * rt;
     for (int m = 0; m < L; ++m) as *= (2.0 * m + 1.0) * h;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
                 const double k0[3] = {-(bx * AB[0] + dx * CD[0]) * ie, -(bx * AB[1] + dx * CD[1]) * ie,
                                       -(bx * AB[2] + dx * CD[2]) * ie};
                 double Fm[9];
-                boys_rt(p.boys, T, Kab * Kcd * rs, p.L, Fm);
+                boys_rt(p.boys, p.boys_inv, T, Kab * Kcd * rs, p.L, Fm);
                 __syncwarp();                              // previous accumulate has read S
                 if (lane <= p.L) B[lane] = Fm[lane];
                 __syncwarp();
@@ -425,6 +427,7 @@ int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cuda
     for (int i = 0; i < c.nxfer; ++i) c.xfer[i] = P->xfer[i];
     for (int i = 0; i < c.nhrr; ++i) c.hrr[i] = P->hrr[i];
     c.acc = P->acc;
+    for (int k = 0; k < QBX_BOYS_DEG; ++k) c.boys_inv[k] = 1.0 / (2.0 * (P->L + k) + 1.0);
     const size_t smem = (size_t)COOP_WARPS * P->buf_doubles * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {

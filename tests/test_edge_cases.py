@@ -1,0 +1,95 @@
+"""Edge cases of the hot path at the C-ABI boundary: degenerate, ragged and extreme inputs.
+
+Every case is checked against the CPU oracle (full tensor and getGcore in all three modes, and
+sharded over ranks where it says so).  The same cases run twice: on the B200 box through
+libqbx.so (`-m gpu`) and here, without a GPU, through the kernels compiled against the cuemu
+host emulation of the CUDA execution model (tests/emu.py; a functional check of the CUDA
+sources, not a product path)."""
+import numpy as np
+import pytest
+
+import emu
+import oracle
+import quiqbox_b200 as qb
+
+
+@pytest.fixture(params=[pytest.param("gpu", marks=pytest.mark.gpu), "emulated"])
+def backend(request):
+    if request.param == "emulated":
+        emu.install()
+        yield request.param
+        emu.uninstall()
+    else:
+        yield request.param
+
+
+def shell(center, xpns, cons, l):
+    return [qb.genGaussTypeOrb(center, xpns, cons, ijk) for ijk in qb.SubshellXYZs(l)]
+
+
+def rand_sym(n, seed):
+    a = np.random.RandomState(seed).uniform(-1, 1, (n, n))
+    return (a + a.T) / 2
+
+
+O, H = (0.0, 0.0, 0.0), (1.4, 0.3, -0.2)
+_MIX = shell(O, [2.0, 0.5], [0.4, 0.7], 0) + shell(O, [1.1], [1.0], 1) + shell(H, [0.9], [1.0], 2) + shell(H, [0.6], [1.0], 1)
+
+CASES = {
+    # name: (basis, ranks to shard over)
+    "single s primitive": (shell(O, [1.3], [1.0], 0), (1,)),
+    "single d shell": (shell(O, [0.8], [1.0], 2), (1,)),
+    "only d shells on two centres": (shell(O, [0.8], [1.0], 2) + shell(H, [1.7, 0.4], [0.6, 0.5], 2), (1,)),
+    "s p d on one centre (AB = 0)": (shell(O, [2.0, 0.5], [0.4, 0.7], 0) + shell(O, [1.1], [1.0], 1) + shell(O, [0.9], [1.0], 2), (1, 3)),
+    # more s shells on one primitive set than a primitive group holds (eri_group.cu: 3 shells, 9 member pairs)
+    "5 s shells sharing 6 primitives": (sum((shell(O, [50, 12, 4, 1.2, 0.4, 0.1], list(np.random.RandomState(k).uniform(-1, 1, 6)), 0)
+                                             for k in range(5)), []) + shell(H, [3.0, 0.7], [0.3, 0.8], 0) + shell(H, [0.9], [1.0], 1), (1, 2)),
+    "12-term contraction": (shell(O, list(10 ** np.linspace(3, -1, 12)), list(np.linspace(0.1, 1, 12)), 0) + shell(H, [0.8], [1.0], 1), (1,)),
+    "exponents 1e5 and 1e-3": (shell(O, [1e5], [1.0], 0) + shell(O, [1e-3], [1.0], 0) + shell(H, [2e4, 3e-3], [0.5, 0.5], 1), (1,)),
+    "centres 100 and 250 bohr apart (asymptotic Boys)": (shell(O, [1.0], [1.0], 0) + shell((100.0, 0, 0), [1.0], [1.0], 1)
+                                                         + shell((0, 250.0, 0), [0.7], [1.0], 2), (1,)),
+    "more ranks than task chunks": (shell(O, [1.0], [1.0], 0) + shell(H, [1.0], [1.0], 1), (1, 7)),
+    "functions in shuffled order": ([_MIX[i] for i in np.random.RandomState(5).permutation(len(_MIX))], (1, 2)),
+    "incomplete shells (p_x, p_z, d_xx, d_yz only)": ([_MIX[0], _MIX[1], _MIX[3], _MIX[4], _MIX[8], _MIX[10], _MIX[11]], (1,)),
+    "duplicate functions": (_MIX[:4] + _MIX[:4], (1,)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tensor_and_fock_vs_oracle(backend, name):
+    bs, ranks = CASES[name]
+    db = qb.DeviceBasis(bs)
+    ob = oracle.OracleBasis(db.data)
+    n = db.nbf
+    Tref = ob.eri_tensor(canonical=True)
+    scale = max(1.0, float(np.max(np.abs(Tref))))
+    assert np.max(np.abs(qb.elecRepulsions(db) - Tref)) < 1e-10 * scale          # north-star bar
+    DJ, DK = rand_sym(n, 1), rand_sym(n, 2)
+    Gref = oracle.getGcore(Tref, DJ, DK)
+    gs = max(1.0, float(np.max(np.abs(Gref))))
+    for mode in ("stored", "direct", "dense"):
+        for nr in ranks:
+            if mode == "dense" and nr > 1:
+                continue
+            acc = np.zeros((n, n))
+            for r in range(nr):                                                   # partial G of every rank
+                acc += qb.DeviceERI(db, mode=mode, screen_tol=0.0, rank=r, nranks=nr).getGcore(DJ, [DK])[0]
+            assert np.max(np.abs(acc - Gref)) < 1e-9 * gs, (mode, nr)
+
+
+def test_screening_that_removes_every_quartet(backend):
+    bs = shell(O, [1.0], [1.0], 0) + shell((40.0, 0, 0), [1.0], [1.0], 0)
+    db = qb.DeviceBasis(bs)
+    D = rand_sym(2, 3)
+    for mode in ("stored", "direct"):
+        G = qb.DeviceERI(db, mode=mode, screen_tol=1e3).getGcore(D, [D])[0]          # empty task lists
+        assert np.array_equal(G, np.zeros((2, 2)))
+    assert db.info()["n_quartets"] == 0
+
+
+def test_empty_quartet_list_and_zero_densities(backend):
+    db = qb.DeviceBasis(_MIX)
+    assert qb.elecRepulsionList(db, np.zeros((0, 4), dtype=np.int64)).shape == (0,)
+    Z = np.zeros((db.nbf, db.nbf))
+    G = qb.DeviceERI(db, screen_tol=0.0).getGcore(Z, [Z, Z])
+    assert len(G) == 2 and not np.any(G[0]) and not np.any(G[1])

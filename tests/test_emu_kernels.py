@@ -135,6 +135,34 @@ print("GSUM %.15e" % float(np.sum(G * D)))
     assert abs(vals[0] - vals[1]) < 1e-8 * max(1.0, abs(vals[0]))
 
 
+_FOCK_CODE = r'''
+import numpy as np
+import oracle, quiqbox_b200 as qb
+from molecules import water_cluster
+nuc, xyz = water_cluster(2)
+bs = sum((qb.genGaussTypeOrbSeq(c, s, "6-31G") for s, c in zip(nuc, xyz)), [])
+db = qb.DeviceBasis(bs)
+n = db.nbf
+rng = np.random.RandomState(9)
+DJ = rng.uniform(-1, 1, (n, n)); DJ = (DJ + DJ.T) / 2
+DK = rng.uniform(-1, 1, (n, n)); DK = (DK + DK.T) / 2
+Gref = oracle.getGcore(oracle.OracleBasis(db.data).eri_tensor(canonical=True), DJ, DK)
+for mode in ("stored", "direct"):
+    G = qb.DeviceERI(db, mode=mode, screen_tol=1e-13).getGcore(DJ, [DK])[0]
+    err = float(np.max(np.abs(G - Gref)))
+    print(mode, "ERR", err)
+    assert err < 1e-10
+'''
+
+
+@pytest.mark.parametrize("env", [{}, {"QBX_DIGEST_SEG": "0"}, {"QBX_DIGEST_SPREAD": "1"}, {"QBX_GC": "0"}],
+                         ids=["default", "per-lane-REDs", "task-order-blocks", "no-general-contraction"])
+def test_fock_build_switches_vs_oracle(env):
+    """(H2O)2/6-31G with Schwarz screening (ragged rows: most warps straddle several (bra pair, C)
+    runs): the digestion's A/B switches must all give the oracle's G."""
+    _run_emulated(_FOCK_CODE, env)
+
+
 def test_deadlock_detector_reports_divergent_barrier(tmp_path):
     """The emulator must abort (not hang) on a barrier that not all live lanes reach."""
     src = tmp_path / "dl.cpp"
