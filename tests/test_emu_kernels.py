@@ -105,9 +105,12 @@ assert err < 1e-12
 '''
 
 
-def test_cooperative_kernel_all_classes_vs_oracle():
-    """QBX_COOP_MIN_ACC=0: every s/p/d class through the warp-cooperative kernel."""
-    _run_emulated(_TENSOR_CODE, {"QBX_COOP_MIN_ACC": "0"})
+@pytest.mark.parametrize("order", ["forward", "reverse"])
+def test_cooperative_kernel_all_classes_vs_oracle(order):
+    """QBX_COOP_MIN_ACC=0: every s/p/d class through the warp-cooperative kernel.  Run with the lanes
+    of a warp (and the warps of a block) scheduled in ascending and in descending order: a missing
+    __syncwarp / __syncthreads between a write and another lane's read shows up in one of the two."""
+    _run_emulated(_TENSOR_CODE, {"QBX_COOP_MIN_ACC": "0", "QBX_EMU_LANE_ORDER": order})
 
 
 def test_general_contraction_sharing_on_off():
@@ -155,8 +158,9 @@ for mode in ("stored", "direct"):
 '''
 
 
-@pytest.mark.parametrize("env", [{}, {"QBX_DIGEST_SEG": "0"}, {"QBX_DIGEST_SPREAD": "1"}, {"QBX_GC": "0"}],
-                         ids=["default", "per-lane-REDs", "task-order-blocks", "no-general-contraction"])
+@pytest.mark.parametrize("env", [{}, {"QBX_EMU_LANE_ORDER": "reverse"}, {"QBX_DIGEST_SEG": "0"}, {"QBX_DIGEST_SPREAD": "1"},
+                                 {"QBX_GC": "0"}],
+                         ids=["default", "reverse-lane-order", "per-lane-REDs", "task-order-blocks", "no-general-contraction"])
 def test_fock_build_switches_vs_oracle(env):
     """(H2O)2/6-31G with Schwarz screening (ragged rows: most warps straddle several (bra pair, C)
     runs): the digestion's A/B switches must all give the oracle's G."""

@@ -68,6 +68,7 @@ static void *g_sched_sp = nullptr;
 static Thread *g_running = nullptr;
 static KernelBody *g_body = nullptr;
 static std::mutex g_launch_mutex;
+static const bool g_reverse = [] { const char *e = getenv("QBX_EMU_LANE_ORDER"); return e && e[0] == 'r'; }();
 
 int sm_count()
 {
@@ -165,11 +166,17 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, KernelBody &body)
         for (;;) {
             bool progress = false;
             size_t live_block = 0, wait_block = 0;
-            for (size_t w = 0; w < nwarp; ++w) {
+            for (size_t wn = 0; wn < nwarp; ++wn) {
+                const size_t w = g_reverse ? nwarp - 1 - wn : wn;          // warps too: missing __syncthreads
                 const size_t lo = w * 32, hi = lo + 32 < nthr ? lo + 32 : nthr;
                 for (;;) {
-                    for (size_t i = lo; i < hi; ++i)
+                    // lane order inside a warp: ascending, or descending with QBX_EMU_LANE_ORDER=reverse.
+                    // Code that is correct under both orders has no missing __syncwarp between a lane's
+                    // write and another lane's read of the same shared location (either direction).
+                    for (size_t n = 0; n < hi - lo; ++n) {
+                        const size_t i = g_reverse ? hi - 1 - n : lo + n;
                         if (g_threads[i].state == RUN) { resume(g_threads[i]); progress = true; }
+                    }
                     unsigned live = 0, waiting = 0, mask = 0;
                     for (size_t i = lo; i < hi; ++i) {
                         const int s = g_threads[i].state;
