@@ -1,0 +1,45 @@
+#!/bin/bash
+# One gpurun call that measures everything changed without a GPU at the end of round 1
+# (segmented digestion reductions, 2-load Boys table, cooperative kernel) and leaves the evidence
+# in gpurun_out/ (copy the summaries you keep into profiles/rNN/):
+#
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_probe.sh'
+#
+# Steps: GPU parity tests -> bench default -> digestion A/B (QBX_DIGEST_SEG=0) -> spread sweep ->
+# ncu launch list of the bench command -> ncu --set full of the digestion / group / cooperative kernels.
+set -u
+OUT=gpurun_out/probe
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.txt" 2>&1
+
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -x -q -m gpu > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" | tee -a "$OUT/pytest_gpu.log"
+tail -3 "$OUT/pytest_gpu.log"
+
+echo "== bench (default flags)"
+timeout 600 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; tail -c 600 "$OUT/bench_default.json"
+echo "== bench --steps 10 (no e2e, no cpu leg)"
+timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10.json" 2> "$OUT/bench_s10.err"
+echo "== digestion A/B: per-lane REDs on non-uniform warps (round-1 behaviour)"
+QBX_DIGEST_SEG=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10_seg0.json" 2> "$OUT/bench_s10_seg0.err"
+for s in 96 384 1536; do
+  QBX_DIGEST_SPREAD=$s timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_spread$s.json" 2>/dev/null
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/probe/bench_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("/")[-1], "ms/step %.2f  eri %.2f  fock %.2f  frac %.3f" % (d["ms_per_step"], d["eri_ms"], d["fock_build_ms"], d["roofline"]["all_eri_kernels_frac"]))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
+    python bench.py --steps 2 --warmup 1 --no-e2e --cpu-seconds 0.2 > "$OUT/ncu_launches.log" 2>&1
+echo "== ncu --set full: digestion, group and cooperative kernels of one store + Fock build"
+timeout 1200 ncu --set full --clock-control none --import-source on \
+    --kernel-name regex:"digest_kernel|eri_group_kernel|eri_coop" --launch-skip 47 --launch-count 47 \
+    -o "$OUT/full_r02" python tools/e2e_probe.py 2 > "$OUT/ncu_full.log" 2>&1
+ls -la "$OUT"
