@@ -17,6 +17,7 @@
 // read coalesced.  One kernel therefore serves every class (and compiles in seconds); the
 // arithmetic is the same sequence of operations as in eri_class.cuh.
 #include <algorithm>
+#include <cstdio>
 #include <map>
 #include <vector>
 
@@ -276,6 +277,35 @@ __device__ __forceinline__ Op ld_op(const Op *ops, int i, int n)
     return o;
 }
 
+// Vertical recurrence of one primitive quartet, table-driven (shared by both cooperative kernels):
+// B[0..L] holds the scaled Boys values on entry, the V region [e0|00]^(m) on exit.
+__device__ __forceinline__ void coop_vrr(const CoopArgs &p, double *B, int lane, const double (&PA)[3], const double (&WP)[3],
+                                         double i2z, double rz)
+{
+    // Entries of one level are independent, so each lane takes COOP_BATCH of them at a
+    // time: all op records first (global, L1/L2), then all sources (shared), then the
+    // arithmetic and the stores -- otherwise every entry pays the full load latency.
+    for (int lv = 0; lv < p.nvrr; ++lv) {
+        const Op *ops = p.ops + p.vrr[lv].first;
+        const int n = p.vrr[lv].count;
+        for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
+            Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH], sc[COOP_BATCH], sd[COOP_BATCH];
+#pragma unroll
+            for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
+#pragma unroll
+            for (int u = 0; u < COOP_BATCH; ++u) {
+                sa[u] = B[o[u].a]; sb[u] = B[o[u].b];
+                sc[u] = o[u].c >= 0 ? B[o[u].c] : 0.0; sd[u] = o[u].c >= 0 ? B[o[u].d] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < COOP_BATCH; ++u)
+                if (i0 + 32 * u < n)
+                    B[o[u].dst] = fma(o[u].n1 * i2z, fma(-rz, sd[u], sc[u]), fma(PA[o[u].ax], sa[u], WP[o[u].ax] * sb[u]));
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
 {
     extern __shared__ double smem[];
@@ -314,25 +344,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
                 // Entries of one level are independent, so each lane takes COOP_BATCH of them at a
                 // time: all op records first (global, L1/L2), then all sources (shared), then the
                 // arithmetic and the stores -- otherwise every entry pays the full load latency.
-                for (int lv = 0; lv < p.nvrr; ++lv) {
-                    const Op *ops = p.ops + p.vrr[lv].first;
-                    const int n = p.vrr[lv].count;
-                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
-                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH], sc[COOP_BATCH], sd[COOP_BATCH];
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) {
-                            sa[u] = B[o[u].a]; sb[u] = B[o[u].b];
-                            sc[u] = o[u].c >= 0 ? B[o[u].c] : 0.0; sd[u] = o[u].c >= 0 ? B[o[u].d] : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u)
-                            if (i0 + 32 * u < n)
-                                B[o[u].dst] = fma(o[u].n1 * i2z, fma(-rz, sd[u], sc[u]), fma(PA[o[u].ax], sa[u], WP[o[u].ax] * sb[u]));
-                    }
-                    __syncwarp();
-                }
+                coop_vrr(p, B, lane, PA, WP, i2z, rz);
                 for (int lv = 0; lv < p.nxfer; ++lv) {
                     const Op *ops = p.ops + p.xfer[lv].first;
                     const int n = p.xfer[lv].count;
@@ -398,6 +410,260 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Second-generation cooperative kernel (compiled per class): only the vertical recurrence is still
+// table-driven.  ncu on the interpreter above (profiles/r01): issue slots 61 % busy with the FP64
+// pipe at 12 % -- ~40 instructions per recurrence entry, most of them fetching and decoding the op
+// record.  Here the electron transfer, the contraction and both horizontal recurrences are
+// compile-time code in which a LANE owns a stacked bra component g = (e, i, j, k) and the ket
+// components are unrolled:
+//   * transfer  [g|cf] <- k0[ax] [g|cf1] - (zeta/eta) [g+1_ax|cf1] + n_ax/(2 eta) [g-1_ax|cf1]
+//                        + nf/(2 eta) [g|cf2]
+//     (cf. modeTransfer, GaussianOrbitals.jl:529-538; same recurrence as EriClass::primitive):
+//     ax, cf1, cf2, nf depend on the ket component only and fold to constants, the neighbours
+//     g+-1_ax are per-lane shared-memory addresses computed once per kernel, so an entry costs
+//     4 LDS + 1 STS + the FP64 work and nothing else;
+//   * the contraction accumulates in registers: the lane that produces [g|cf] adds it to its own
+//     acc[cf] when g is in the contracted range (<= 32 stacked components for every d-rich class);
+//   * horizontal recurrences run on register rows with the thread kernels' hrr_apply: bra with one
+//     lane per stacked ket component, ket with one lane per (a,b) pair, transposed through shared memory.
+// QBX_COOP2=0 routes these classes back to the interpreter (A/B, and the reference for the tests).
+template <int LA, int LB, int LC, int LD>
+struct Coop2 {
+    static constexpr int E = LA + LB, F = LC + LD, L = E + F;
+    static constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NAB = NA * NB;
+    static constexpr int NCOMP = NAB * NCc * ND;
+    static constexpr int NACC = NCSUM(LA, E), NKET = NCSUM(LC, F);
+    static constexpr int GT = S1(L + 1);                       // all stacked bra components, degrees 0..L
+    static constexpr int GB = S1(LA);                          // lane 0 of pass 0 owns the first contracted component
+    static_assert(F >= 1 && NACC <= 32 && NKET <= 32, "Coop2: class outside the layout's assumptions");
+    // transfer level f keeps degrees e in [elo(f), ehi(f)] = global stacked range [glo(f), ghi(f))
+    static __host__ __device__ constexpr int elo(int f) { return (LA - (F - f)) > 0 ? (LA - (F - f)) : 0; }
+    static __host__ __device__ constexpr int ehi(int f) { return E + (F - f); }
+    static __host__ __device__ constexpr int glo(int f) { return S1(elo(f)); }
+    static __host__ __device__ constexpr int ghi(int f) { return S1(ehi(f) + 1); }
+    static __host__ __device__ constexpr int rl(int f) { return ghi(f) - glo(f); }
+    static constexpr int VT = VLay<L>::total;                  // V region: [e0|00]^(m), layout of VLay<L>
+    static __host__ __device__ constexpr int woff(int f)       // level f: [cf][g - glo(f)], level 0 = V at m = 0, stacked
+    {
+        int o = VT;
+        for (int x = 0; x < f; ++x) o += NC(x) * rl(x);
+        return o;
+    }
+    static constexpr int WT = woff(F + 1);
+    // after the primitive loops the W levels are dead: ACC2[kk][ASTR] and X2[ab][XSTR] (odd strides) go there
+    static constexpr int ASTR = NACC | 1, XSTR = NKET | 1;
+    static constexpr int acc2_off = VT, x2_off = VT + NKET * ASTR;
+    static constexpr int BUF = (WT > x2_off + NAB * XSTR ? WT : x2_off + NAB * XSTR);
+    // passes: q < NPH owns g = GB + 32 q + lane; the last pass (only if GB > 0) owns g = lane < GB
+    static constexpr int NPH = (GT - GB + 31) / 32;
+    static constexpr int NP = NPH + (GB > 0 ? 1 : 0);
+    static __host__ __device__ constexpr int pass_lo(int q) { return q < NPH ? GB + 32 * q : 0; }
+    static __host__ __device__ constexpr int pass_hi(int q) { return q < NPH ? (GB + 32 * q + 32 < GT ? GB + 32 * q + 32 : GT) : GB; }
+    // passes that hold targets of some transfer level >= 1 (the others only take part in the level-0 copy)
+    static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return pass_lo(q) < ghi(f) && pass_hi(q) > glo(f); }
+    static __host__ __device__ constexpr bool pass_has_info(int q) { return pass_in_level(q, 1); }
+
+    struct LaneInfo {            // per pass
+        int g;                   // own stacked index (or -1: lane idle in this pass)
+        const double *v0;        // [g|0]^(0) in the V region
+        double *gp;              // B + g, B + (g + 1_ax), B + (g - 1_ax): a level's row start (a constant) is added
+        const double *up[3], *dn[3];   //   at the point of use, so every access is one LDS/STS with an immediate offset
+        double n[3];             // (i, j, k) of g
+    };
+
+    static __device__ __forceinline__ void lane_info(int q, int lane, double *B, LaneInfo &I)
+    {
+        const int g = pass_lo(q) + lane;
+        I.g = g < pass_hi(q) ? g : -1;
+        int e = 0;
+        while (e < L && S1(e + 1) <= g) ++e;
+        const int c = g - S1(e);
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= c) ++r;
+        const int k = c - r * (r + 1) / 2, j = r - k, i = e - r;
+        I.v0 = B + VLay<L>::off(e) + c;
+        I.gp = B + g;
+        I.up[0] = B + S1(e + 1) + CIDX(j, k); I.up[1] = B + S1(e + 1) + CIDX(j + 1, k); I.up[2] = B + S1(e + 1) + CIDX(j, k + 1);
+        I.dn[0] = B + (i > 0 ? S1(e - 1) + CIDX(j, k) : g);
+        I.dn[1] = B + (j > 0 ? S1(e - 1) + CIDX(j - 1, k) : g);
+        I.dn[2] = B + (k > 0 ? S1(e - 1) + CIDX(j, k - 1) : g);
+        I.n[0] = i; I.n[1] = j; I.n[2] = k;
+        if (I.g < 0) { I.v0 = B; I.gp = B; for (int x = 0; x < 3; ++x) { I.up[x] = I.dn[x] = B; I.n[x] = 0.0; } }
+    }
+
+    // build level FL + 1 from FL (and FL - 1), then recurse
+    template <int FL>
+    static __device__ __forceinline__ void transfer(const LaneInfo (&I)[NP], const double (&nae)[NP][3],
+                                                    const double (&k0)[3], double zoe, double i2e, double (&acc)[NKET], int lane)
+    {
+        if constexpr (FL < F) {
+            constexpr int f1 = FL + 1;
+#pragma unroll
+            for (int rf = 0; rf <= f1; ++rf)
+#pragma unroll
+                for (int kf = 0; kf <= rf; ++kf) {
+                    const int fi = f1 - rf, fj = rf - kf;
+                    const int ax = fi > 0 ? 0 : (fj > 0 ? 1 : 2);
+                    const int fj1 = fj - (ax == 1), fk1 = kf - (ax == 2);
+                    const int nf = (ax == 0 ? fi : (ax == 1 ? fj : kf)) - 1;
+                    const int cf = CIDX(fj, kf), cf1 = CIDX(fj1, fk1);
+                    const int cf2 = nf > 0 ? CIDX(fj1 - (ax == 1), fk1 - (ax == 2)) : 0;
+                    // row starts relative to B + g (compile-time constants once the loops are unrolled)
+                    const int src = woff(FL) + cf1 * rl(FL) - glo(FL);
+                    const int src2 = woff(FL > 0 ? FL - 1 : 0) + cf2 * rl(FL > 0 ? FL - 1 : 0) - glo(FL > 0 ? FL - 1 : 0);
+                    const int dst = woff(f1) + cf * rl(f1) - glo(f1);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        if (!pass_in_level(q, f1)) continue;
+                        const int g = I[q].g;
+                        if (g >= glo(f1) && g < ghi(f1)) {
+                            double v = fma(k0[ax], I[q].gp[src], -zoe * I[q].up[ax][src]);
+                            v = fma(nae[q][ax], I[q].dn[ax][src], v);
+                            if (nf > 0) v = fma(nf * i2e, I[q].gp[src2], v);
+                            I[q].gp[dst] = v;
+                            if (f1 >= LC && q == 0 && lane < NACC) acc[NCSUM(LC, f1 - 1) + cf] += v;
+                        }
+                    }
+                }
+            __syncwarp();
+            transfer<FL + 1>(I, nae, k0, zoe, i2e, acc, lane);
+        }
+    }
+};
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop2_kernel(CoopArgs p)
+{
+    using C2 = Coop2<LA, LB, LC, LD>;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *B = smem + (size_t)wib * C2::BUF;
+    typename C2::LaneInfo I[C2::NP];
+#pragma unroll
+    for (int q = 0; q < C2::NP; ++q) C2::lane_info(q, lane, B, I[q]);
+    const int64_t warp0 = (int64_t)blockIdx.x * COOP_WARPS + wib, nwarps = (int64_t)gridDim.x * COOP_WARPS;
+    for (int64_t qt = warp0; qt < p.ntasks; qt += nwarps) {
+        const int2 t = p.tasks[qt];
+        const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
+        const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
+        const double CD[3] = {gk[3], gk[4], gk[5]};
+        const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
+        const int pk0 = p.ket.prim_off[t.y], pk1 = p.ket.prim_off[t.y + 1];
+        double acc[C2::NKET];
+#pragma unroll
+        for (int i = 0; i < C2::NKET; ++i) acc[i] = 0.0;
+        for (int pb = pb0; pb < pb1; ++pb) {
+            const double *rb = p.bra.prim + 8 * (int64_t)pb;
+            const double zeta = __ldg(rb), P[3] = {__ldg(rb + 1), __ldg(rb + 2), __ldg(rb + 3)};
+            const double Kab = __ldg(rb + 4), bx = __ldg(rb + 5), i2z = __ldg(rb + 6);
+            const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+            for (int pk = pk0; pk < pk1; ++pk) {
+                const double *rk = p.ket.prim + 8 * (int64_t)pk;
+                const double eta = __ldg(rk), Q[3] = {__ldg(rk + 1), __ldg(rk + 2), __ldg(rk + 3)};
+                const double Kcd = __ldg(rk + 4), dx = __ldg(rk + 5), i2e = __ldg(rk + 6);
+                const double rs = rsqrt(zeta + eta), inv = rs * rs, rz = eta * inv;
+                const double PQ[3] = {P[0] - Q[0], P[1] - Q[1], P[2] - Q[2]};
+                const double T = zeta * rz * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+                const double WP[3] = {-rz * PQ[0], -rz * PQ[1], -rz * PQ[2]};
+                const double ie = 2.0 * i2e, zoe = zeta * ie;
+                const double k0[3] = {-(bx * AB[0] + dx * CD[0]) * ie, -(bx * AB[1] + dx * CD[1]) * ie,
+                                      -(bx * AB[2] + dx * CD[2]) * ie};
+                double Fm[9];
+                boys_rt(p.boys, p.boys_inv, T, Kab * Kcd * rs, C2::L, Fm);
+                __syncwarp();                              // the previous primitive's level-0 copy has read V
+                if (lane <= C2::L) B[lane] = Fm[lane];
+                __syncwarp();
+                coop_vrr(p, B, lane, PA, WP, i2z, rz);
+                // level 0 of the transfer = V at m = 0, copied into the stacked layout
+                double nae[C2::NP][3];
+#pragma unroll
+                for (int q = 0; q < C2::NP; ++q) {
+                    const int g = I[q].g;
+                    if (g >= C2::glo(0)) I[q].gp[C2::woff(0) - C2::glo(0)] = *I[q].v0;
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) nae[q][x] = I[q].n[x] * i2e;
+                }
+                if constexpr (LC == 0) {
+                    if (lane < C2::NACC) acc[0] += *I[0].v0;
+                }
+                __syncwarp();
+                C2::template transfer<0>(I, nae, k0, zoe, i2e, acc, lane);
+            }
+        }
+        // contracted [e0|f0] -> shared, one row per stacked ket component
+        __syncwarp();
+        if (lane < C2::NACC) {
+#pragma unroll
+            for (int kk = 0; kk < C2::NKET; ++kk) B[C2::acc2_off + kk * C2::ASTR + lane] = acc[kk];
+        }
+        __syncwarp();
+        // bra horizontal recurrence: lane = stacked ket component
+        if (lane < C2::NKET) {
+            const double *row = B + C2::acc2_off + lane * C2::ASTR;
+            hrr_apply<LA, LB>([&](int e, int c) { return row[S1(e) - S1(LA) + c]; }, AB,
+                              [&](int a, int b, double v) { B[C2::x2_off + (a * C2::NB + b) * C2::XSTR + lane] = v; });
+        }
+        __syncwarp();
+        // ket horizontal recurrence: lane = (a, b); weights; store (component-major)
+        const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
+        const double *sA = p.shell_scale + 6 * sb.x, *sB = p.shell_scale + 6 * sb.y;
+        const double *sC = p.shell_scale + 6 * sk.x, *sD = p.shell_scale + 6 * sk.y;
+        for (int ab = lane; ab < C2::NAB; ab += 32) {
+            const double *row = B + C2::x2_off + ab * C2::XSTR;
+            const double sab = sA[ab / C2::NB] * sB[ab % C2::NB];
+            hrr_apply<LC, LD>([&](int f, int c) { return row[NCSUM(LC, f - 1) + c]; }, CD,
+                              [&](int c, int d, double v) {
+                                  p.out[(int64_t)((ab * C2::NCc + c) * C2::ND + d) * p.ntasks + qt] = v * sab * sC[c] * sD[d];
+                              });
+        }
+        __syncwarp();
+    }
+}
+
+typedef int (*Coop2Launch)(const CoopArgs &, int64_t, cudaStream_t);
+
+template <int LA, int LB, int LC, int LD>
+int launch_coop2(const CoopArgs &c, int64_t ntasks, cudaStream_t s)
+{
+    using C2 = Coop2<LA, LB, LC, LD>;
+    const size_t smem = (size_t)COOP_WARPS * C2::BUF * sizeof(double);
+    static int per_sm = 0, sms = 0;
+    if (per_sm == 0) {
+        int dev = 0;
+        QBX_CUDA(cudaFuncSetAttribute(eri_coop2_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QBX_CUDA(cudaGetDevice(&dev));
+        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_coop2_kernel<LA, LB, LC, LD>, COOP_WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int64_t need = (ntasks + COOP_WARPS - 1) / COOP_WARPS, cap = (int64_t)sms * per_sm;
+    static const bool trace = getenv("QBX_TRACE_COOP") != nullptr;
+    if (trace) fprintf(stderr, "[qbx] coop2 (%d%d|%d%d): %lld quartets, %zu B shared per block, %d blocks/SM\n", LA, LB, LC, LD,
+                       (long long)ntasks, smem, per_sm);
+    eri_coop2_kernel<LA, LB, LC, LD><<<(unsigned)std::min(need, cap), COOP_WARPS * 32, smem, s>>>(c);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
+
+// classes compiled for the second-generation kernel: everything the thread kernels do not serve, plus
+// the two thread-kernel classes that spill at 255 registers ((dp|pp), (dp|ds))
+Coop2Launch coop2_for(int la, int lb, int lc, int ld)
+{
+    const int key = la * 1000 + lb * 100 + lc * 10 + ld;
+    switch (key) {
+        case 2121: return launch_coop2<2, 1, 2, 1>;
+        case 2211: return launch_coop2<2, 2, 1, 1>;
+        case 2220: return launch_coop2<2, 2, 2, 0>;
+        case 2221: return launch_coop2<2, 2, 2, 1>;
+        case 2222: return launch_coop2<2, 2, 2, 2>;
+        case 2111: return launch_coop2<2, 1, 1, 1>;
+        case 2120: return launch_coop2<2, 1, 2, 0>;
+        default: return nullptr;
+    }
+}
+
 std::map<int, Program *> g_programs;
 
 }  // namespace
@@ -428,6 +694,10 @@ int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cuda
     for (int i = 0; i < c.nhrr; ++i) c.hrr[i] = P->hrr[i];
     c.acc = P->acc;
     for (int k = 0; k < QBX_BOYS_DEG; ++k) c.boys_inv[k] = 1.0 / (2.0 * (P->L + k) + 1.0);
+    static const int use2 = getenv("QBX_COOP2") ? atoi(getenv("QBX_COOP2")) : 1;
+    if (use2) {
+        if (Coop2Launch f = coop2_for(la, lb, lc, ld)) return f(c, a.ntasks, s);
+    }
     const size_t smem = (size_t)COOP_WARPS * P->buf_doubles * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
