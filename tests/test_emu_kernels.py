@@ -113,6 +113,11 @@ def test_cooperative_kernel_all_classes_vs_oracle(order):
     _run_emulated(_TENSOR_CODE, {"QBX_COOP_MIN_ACC": "0", "QBX_EMU_LANE_ORDER": order})
 
 
+def test_cooperative_kernel_generations_agree(monkeypatch):
+    monkeypatch.setenv("QBX_TEST_BOOT", "import emu; emu.install()")
+    P.test_cooperative_kernel_generations_agree()
+
+
 def test_general_contraction_sharing_on_off():
     """(H2O)2/cc-pVDZ with Schwarz screening: the group kernels (QBX_GC=1, default) and the plain
     class kernels (QBX_GC=0) must give the same Fock matrix, and both must match the oracle tensor."""
