@@ -32,6 +32,25 @@ static int launch_eri(const ClassArgs &a, cudaStream_t s)
     return QBX_OK;
     }
 }
+// warp-per-task variant, instantiated for the diagonal classes (ab|ab) only: the Schwarz pass
+static int launch_eri_split(const ClassArgs &a, cudaStream_t s)
+{
+    if constexpr (QLA == QLC && QLB == QLD && NCSUM(QLA, QLA + QLB) * NCSUM(QLC, QLC + QLD) < QBX_COOP_ACC) {
+        if (a.ntasks <= 0) return QBX_OK;
+        int dev = 0, sms = 0;
+        QBX_CUDA(cudaGetDevice(&dev));
+        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t need = (a.ntasks + QBX_ERI_THREADS / 32 - 1) / (QBX_ERI_THREADS / 32);
+        const int64_t cap = (int64_t)sms * 4;
+        eri_class_split_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(need < cap ? need : cap), QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
+        QBX_CUDA(cudaGetLastError());
+        return QBX_OK;
+    } else {
+        (void)a; (void)s;
+        qbx_set_error("internal: no warp-per-task kernel for this class");
+        return QBX_ERR_STATE;
+    }
+}
 static int launch_digest(const DigestArgs &a, cudaStream_t s)
 {
     if (a.ntasks <= 0) return QBX_OK;
@@ -53,4 +72,6 @@ static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 extern const ClassOps QBX_CAT(QLA, QLB, QLC, QLD);
 const ClassOps QBX_CAT(QLA, QLB, QLC, QLD) = {QLA, QLB, QLC, QLD,
                                               EriClass<QLA, QLB, QLC, QLD>::NCOMP,
-                                              launch_eri, launch_digest, launch_scatter};
+                                              launch_eri, launch_digest, launch_scatter,
+                                              (QLA == QLC && QLB == QLD && NCSUM(QLA, QLA + QLB) * NCSUM(QLC, QLC + QLD) < QBX_COOP_ACC)
+                                                  ? launch_eri_split : nullptr};

@@ -649,7 +649,14 @@ int Engine::ensure_schwarz(cudaStream_t s)
         QBX_CUDA(qbx_dmalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
         scratch.push_back(t); scratch.push_back(v);
         k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, cs>>>(P.npair, t);
-        if ((rc = run_eri(pc, pc, t, P.npair, v, cs))) return rc;
+        // a diagonal (ab|ab) of two long contractions is thousands of primitive quartets: one WARP per pair
+        // (QBX_SCHWARZ_SPLIT=0: one thread per pair, the first version)
+        static const int split = getenv("QBX_SCHWARZ_SPLIT") ? atoi(getenv("QBX_SCHWARZ_SPLIT")) : 1;
+        if (split && ops->eri_split) {
+            ClassArgs a;
+            if ((rc = eri_args(pc, pc, t, P.npair, v, cs, a))) return rc;
+            if ((rc = ops->eri_split(a, cs))) return rc;
+        } else if ((rc = run_eri(pc, pc, t, P.npair, v, cs))) return rc;
         const int nab = qbx_nc(P.la) * qbx_nc(P.lb);
         k_schwarz<<<(P.npair + 127) / 128, 128, 0, cs>>>(v, P.npair, nab, P.schwarz);
         QBX_CUDA(cudaGetLastError());

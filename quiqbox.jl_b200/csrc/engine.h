@@ -44,6 +44,7 @@ struct ClassOps {
     int (*eri)(const ClassArgs &, cudaStream_t);
     int (*digest)(const DigestArgs &, cudaStream_t);
     int (*scatter)(const ScatterArgs &, cudaStream_t);
+    int (*eri_split)(const ClassArgs &, cudaStream_t);     // one warp per task (diagonal classes only, else null)
 };
 const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
 

@@ -348,3 +348,54 @@ __global__ void __launch_bounds__(QBX_ERI_THREADS, (LA + LB + LC + LD <= 2 ? 3 :
                    p.shell_scale + 6 * sk.y, p.out + q, p.ntasks);
     }
 }
+
+// One WARP per task, the lanes split the ket primitives and meet in a shuffle reduction: for SHORT lists of
+// HEAVY tasks, i.e. the Schwarz diagonals (ab|ab).  A lone thread needs ~800 cycles per primitive quartet (one
+// dependent chain), so with one task per thread the 6561 primitive quartets of a (9s 9s|9s 9s) diagonal set the
+// duration of the whole Schwarz pass (3.3 ms of a 61 ms create -> store -> Fock build step) while the GPU idles.
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(QBX_ERI_THREADS) eri_class_split_kernel(ClassArgs p)
+{
+    using EC = EriClass<LA, LB, LC, LD>;
+    extern __shared__ double boys_smem[];
+    boys_stage_smem<EC::L>(p.boys, boys_smem);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp0; q < p.ntasks; q += nwarps) {
+        const int2 t = p.tasks[q];
+        const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
+        const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
+        const double CD[3] = {gk[3], gk[4], gk[5]};
+        const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
+        const int nk = p.ket.prim_off[t.y + 1] - p.ket.prim_off[t.y];
+        const int2 si = p.ket.soa_idx[t.y];
+        double acc[EC::AL::total];
+#pragma unroll
+        for (int i = 0; i < EC::AL::total; ++i) acc[i] = 0.0;
+        for (int pk = lane; pk < nk; pk += 32) {
+            const double *kp = p.ket.soa + si.x + (int64_t)pk * QBX_SOA_NF * si.y;
+            const double eta = __ldg(kp);
+            const double Q[3] = {__ldg(kp + si.y), __ldg(kp + 2 * si.y), __ldg(kp + 3 * si.y)};
+            const double Kcd = __ldg(kp + 4 * si.y), dx = __ldg(kp + 5 * si.y), i2e = __ldg(kp + 6 * si.y);
+            const double dCD[3] = {dx * CD[0], dx * CD[1], dx * CD[2]};
+            for (int pb = pb0; pb < pb1; ++pb) {
+                const double4 b0 = ldg4(p.bra.prim + 8 * (int64_t)pb);
+                const double4 b1 = ldg4(p.bra.prim + 8 * (int64_t)pb + 4);
+                const double zeta = b0.x, P[3] = {b0.y, b0.z, b0.w}, Kab = b1.x, i2z = b1.z;
+                const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+                const double bAB[3] = {b1.y * AB[0], b1.y * AB[1], b1.y * AB[2]};
+                EC::primitive(acc, boys_smem, zeta, P, Kab, PA, i2z, bAB, eta, Q, Kcd, i2e, dCD);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < EC::AL::total; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) {
+            const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
+            EC::finish(acc, AB, CD, p.shell_scale + 6 * sb.x, p.shell_scale + 6 * sb.y, p.shell_scale + 6 * sk.x,
+                       p.shell_scale + 6 * sk.y, p.out + q, p.ntasks);
+        }
+    }
+}

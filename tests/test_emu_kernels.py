@@ -160,12 +160,15 @@ for mode in ("stored", "direct"):
     err = float(np.max(np.abs(G - Gref)))
     print(mode, "ERR", err)
     assert err < 1e-10
+print("NQ", db.info()["n_quartets"])
+assert db.info()["n_quartets"] == 13652        # Schwarz bounds do not depend on which kernel computed the diagonals
 '''
 
 
 @pytest.mark.parametrize("env", [{}, {"QBX_EMU_LANE_ORDER": "reverse"}, {"QBX_DIGEST_SEG": "0"}, {"QBX_DIGEST_SPREAD": "1"},
-                                 {"QBX_GC": "0"}],
-                         ids=["default", "reverse-lane-order", "per-lane-REDs", "task-order-blocks", "no-general-contraction"])
+                                 {"QBX_GC": "0"}, {"QBX_SCHWARZ_SPLIT": "0"}],
+                         ids=["default", "reverse-lane-order", "per-lane-REDs", "task-order-blocks", "no-general-contraction",
+                              "schwarz-thread-per-pair"])
 def test_fock_build_switches_vs_oracle(env):
     """(H2O)2/6-31G with Schwarz screening (ragged rows: most warps straddle several (bra pair, C)
     runs): the digestion's A/B switches must all give the oracle's G."""
