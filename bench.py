@@ -332,9 +332,26 @@ def main():
                 traffic = tj["dram_bytes_per_launch"].get(f"eri_class_kernel<{code // 1000},{code // 100 % 10},{code // 10 % 10},{code % 10}>")
         except Exception:
             pass
+        def kernel_name(code):
+            la, lb, lc, ld = code // 1000, code // 100 % 10, code // 10 % 10, code % 10
+            nacc = ((la + lb + 1) * (la + lb + 2) * (la + lb + 3) // 6 - la * (la + 1) * (la + 2) // 6) * \
+                   ((lc + ld + 1) * (lc + ld + 2) * (lc + ld + 3) // 6 - lc * (lc + 1) * (lc + 2) // 6)
+            if nacc >= 180:                                   # QBX_COOP_ACC: warp-cooperative kernels
+                return (f"eri_coop2_kernel<{la},{lb},{lc},{ld}>" if os.environ.get("QBX_COOP2", "1") != "0"
+                        else "eri_coop_kernel")
+            if lb == 0 and lc == 0 and ld == 0 and la <= 1 and os.environ.get("QBX_GC", "1") != "0":
+                return f"eri_group_kernel<{la}>"              # ket-side general-contraction sharing
+            return f"eri_class_kernel<{la},{lb},{lc},{ld}>"
+        try:
+            if traffic is None and tj["workload"] == label and world == tj["n_gpus"]:
+                traffic = tj["dram_bytes_per_launch"].get(kernel_name(code))
+        except Exception:
+            pass
+        switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_COOP2", "QBX_COOP_MIN_ACC", "QBX_DIGEST_SEG", "QBX_DIGEST_SPREAD",
+                                               "QBX_SCHWARZ_SPLIT", "QBX_POOL_GB") if k in os.environ}
         per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
                       "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],
-                      "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0} for r in cls if r[2] > 0]
+                      "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0, "kernel": kernel_name(int(r[0]))} for r in cls if r[2] > 0]
         line = {
             "metric": METRIC, "value": tot_values / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
@@ -342,10 +359,11 @@ def main():
             "config": {"workload": label, "nbf": n, "shells": info["nshell"], "unique_shell_quartets": tot_quartets,
                        "unique_eris": tot_values, "prim_quartets": tot_primq, "screen_tol": args.screen,
                        "l2": "inputs larger than L2 (packed store %.1f GB/rank)" % (info["stored_bytes"] * 1e-9),
-                       "parallelism": f"shell-quartet shards x{world}", "setup_seconds": setup_s},
+                       "parallelism": f"shell-quartet shards x{world}", "setup_seconds": setup_s,
+                       "switches": switches or "defaults"},
             "eri_ms": eri_ms_max, "fock_build_ms": fock_max, "fock_build_s_per_iter": fock_max * 1e-3,
             "gpu_launches": int(round((st1["launches"] - st0["launches"]))),
-            "roofline": {"bound": "fp64", "kernel": f"eri_class_kernel<{code // 1000},{code // 100 % 10},{code // 10 % 10},{code % 10}>",
+            "roofline": {"bound": "fp64", "kernel": kernel_name(code),
                          "achieved": kflops, "peak": peak.value, "unit": "TFLOP/s", "frac": kflops / peak.value if peak.value else None,
                          "traffic": traffic, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/traffic.json); the kernel is FP64-bound, its DRAM traffic is the packed output plus the task list",
                          "peak_source": "measured in this run (qbx_fp64_peak, DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
