@@ -346,6 +346,7 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
                     big = std::max(big, fabs(cc * r.v[4]));
                 }
                 if (big < 1e-24) continue;
+                if (prims[g].empty()) prims[g].reserve(P.xpn.size() * Q.xpn.size());
                 prims[g].push_back(r);
             }
     }
@@ -364,21 +365,25 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         for (size_t m = 0; m < members[g].size(); ++m) mem[n * QBX_GRP_MAXMEM + m] = members[g][m];
         poff[n + 1] = poff[n] + (int)prims[g].size();
     }
-    std::vector<double> soa((size_t)QBX_GRP_NF * poff.back(), 0.0);
+    std::vector<double> soa((size_t)QBX_GRP_NF * poff.back());     // every element is written below
     std::vector<int2> soa_idx(ng0);
     size_t base = 0, g0 = 0;
     while (g0 < ng0) {
         size_t g1 = g0;
         while (g1 < ng0 && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
         const size_t gs = g1 - g0, np = (size_t)out.h_nprim[g0];
-        for (size_t n = g0; n < g1; ++n) {
-            soa_idx[n] = make_int2((int)(base + (n - g0)), (int)gs);
-            for (size_t pp = 0; pp < np; ++pp)
-                for (int k = 0; k < QBX_GRP_NF; ++k) soa[base + (pp * QBX_GRP_NF + k) * gs + (n - g0)] = prims[order[n]][pp].v[k];
-        }
+        for (size_t n = g0; n < g1; ++n) soa_idx[n] = make_int2((int)(base + (n - g0)), (int)gs);
         base += gs * np * QBX_GRP_NF;
         g0 = g1;
     }
+    qbx_parallel_for(ng0, 16, [&](size_t lo, size_t hi) {          // transposition: groups are independent
+        for (size_t n = lo; n < hi; ++n) {
+            const size_t b0 = (size_t)soa_idx[n].x, gs = (size_t)soa_idx[n].y, np = (size_t)out.h_nprim[n];
+            const Rec *r = prims[order[n]].data();
+            for (size_t pp = 0; pp < np; ++pp)
+                for (int k = 0; k < QBX_GRP_NF; ++k) soa[b0 + (pp * QBX_GRP_NF + k) * gs] = r[pp].v[k];
+        }
+    });
     QBX_CUDA(qbx_dmalloc(&out.nmem, std::max<size_t>(1, ng0) * sizeof(int)));
     QBX_CUDA(qbx_dmalloc(&out.members, std::max<size_t>(1, mem.size()) * sizeof(int)));
     QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));

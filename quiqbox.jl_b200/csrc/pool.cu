@@ -143,3 +143,70 @@ void *qbx_staging(size_t bytes)
     }
     return buf;
 }
+
+// ------------------------------------------------------------------ persistent host workers
+// A fixed set of threads that sleep on a condition variable between calls; one job at a time
+// (qbx_parallel_for is only entered under the library's handle mutex or the staging mutex, a second
+// caller simply waits).  The threads are detached and live until the process ends.
+#include <condition_variable>
+namespace {
+struct HostWorkers {
+    std::mutex job_mu;                        // one job at a time
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    void (*fn)(void *) = nullptr;
+    void *ctx = nullptr;
+    unsigned wanted = 0, started = 0, running = 0;
+    uint64_t epoch = 0;
+    unsigned nthreads = 0;
+    HostWorkers()
+    {
+        nthreads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        for (unsigned t = 1; t < nthreads; ++t) std::thread([this] { loop(); }).detach();
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            void (*f)(void *);
+            void *c;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_start.wait(lk, [&] { return epoch != seen && started < wanted; });
+                seen = epoch;
+                ++started;
+                f = fn; c = ctx;
+            }
+            f(c);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void run(unsigned nt, void (*f)(void *), void *c)
+    {
+        std::lock_guard<std::mutex> job(job_mu);
+        nt = std::min(nt, nthreads);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = f; ctx = c;
+            wanted = nt - 1; started = 0; running = nt - 1;
+            ++epoch;
+        }
+        if (nt > 1) cv_start.notify_all();
+        f(c);                                 // the caller works too
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return running == 0; });
+        wanted = 0;
+    }
+};
+HostWorkers &host_workers()
+{
+    static HostWorkers *w = new HostWorkers;  // never destroyed: detached threads may outlive static destructors
+    return *w;
+}
+}   // namespace
+
+unsigned qbx_host_workers() { return host_workers().nthreads; }
+void qbx_host_workers_run(unsigned nthreads, void (*fn)(void *), void *ctx) { host_workers().run(nthreads, fn, ctx); }

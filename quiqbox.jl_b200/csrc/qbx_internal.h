@@ -41,24 +41,25 @@ void qbx_pool_release();
 void qbx_pool_counts(int64_t *hits, int64_t *misses, int64_t *idle_bytes);
 template <class T> inline cudaError_t qbx_dmalloc(T **p, size_t bytes) { return qbx_pool_malloc((void **)p, bytes); }
 
-// f(lo, hi) over [0, n) on a few host threads, `grain` items at a time
+// f(lo, hi) over [0, n) on a few host threads, `grain` items at a time.  The workers are persistent
+// (pool.cu): a qbx_basis_create makes a dozen of these calls, and spawning seven std::threads for
+// each cost more than the work of the smaller pair classes.
+void qbx_host_workers_run(unsigned nthreads, void (*fn)(void *), void *ctx);     // runs fn(ctx) on nthreads threads (caller included)
+unsigned qbx_host_workers();                                                      // threads available (<= 8)
 template <class F>
 inline void qbx_parallel_for(size_t n, size_t grain, F f)
 {
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), (n + grain - 1) / grain);
+    const unsigned nt = (unsigned)std::min<size_t>(qbx_host_workers(), (n + grain - 1) / grain);
     if (nt <= 1) { f(0, n); return; }
-    std::atomic<size_t> next(0);
-    auto work = [&] {
+    struct Ctx { std::atomic<size_t> next; size_t n, grain; F *f; } ctx{{0}, n, grain, &f};
+    qbx_host_workers_run(nt, [](void *p) {
+        Ctx &c = *static_cast<Ctx *>(p);
         for (;;) {
-            const size_t lo = next.fetch_add(grain);
-            if (lo >= n) return;
-            f(lo, std::min(n, lo + grain));
+            const size_t lo = c.next.fetch_add(c.grain);
+            if (lo >= c.n) return;
+            (*c.f)(lo, std::min(c.n, lo + c.grain));
         }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
+    }, &ctx);
 }
 
 __host__ __device__ constexpr int qbx_nc(int l) { return (l + 1) * (l + 2) / 2; }
