@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--screen", type=float, default=1e-12)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batched", action="store_true",
+                    help="also time the shell-batched algorithm on the host cores (tools/cpu_shell_batched.py, SURVEY.md 8d mode ii)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -382,6 +384,13 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{nd} uniformly sampled contracted ERIs of {label} in {tu:.1f} s, OpenMP over "
                                               "quartets; per-primitive-component algorithm of the reference"}
+        if world == 1 and args.cpu_batched:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import cpu_shell_batched
+                line["cpu_baseline_batched"] = cpu_shell_batched.run()
+            except Exception as exc:                       # a reported extra, never the reason for a missing bench line
+                line["cpu_baseline_batched"] = {"unavailable": str(exc)[-300:]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
