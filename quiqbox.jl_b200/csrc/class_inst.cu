@@ -61,6 +61,34 @@ static int launch_digest(const DigestArgs &a, cudaStream_t s)
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }
+// row-resident digestion; -1 = does not apply here (UHF build, rows too long for shared memory): use launch_digest
+static int launch_digest_rows(const DigestArgs &a0, cudaStream_t s)
+{
+    if (a0.ntasks <= 0) return QBX_OK;
+    const size_t smem = (size_t)digest_rows_doubles<QLA, QLB>(a0.nbf) * sizeof(double);
+    if (a0.nmat != 1 || smem > QBX_ROWS_MAX_SMEM) return -1;
+    static int sms = 0;
+    static size_t attr = 0;
+    if (sms == 0) {
+        int dev = 0;
+        QBX_CUDA(cudaGetDevice(&dev));
+        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (smem > attr) {
+        QBX_CUDA(cudaFuncSetAttribute(digest_rows_kernel<QLA, QLB, QLC, QLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    DigestArgs a = a0;
+    // span: long enough to amortise loading and flushing the rows, short enough to keep every SM busy
+    int64_t span = a.ntasks / ((int64_t)sms * 8);
+    span = span > 2048 ? 2048 : (span < 128 ? 128 : span / 128 * 128);
+    a.span = (int)span;
+    const int64_t nblk = (a.ntasks + span - 1) / span;
+    const int64_t R = nblk < a.spread ? nblk : a.spread, C = (nblk + R - 1) / R;
+    digest_rows_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(R * C), 128, smem, s>>>(a);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
 static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 {
     if (a.ntasks <= 0) return QBX_OK;
@@ -72,6 +100,6 @@ static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 extern const ClassOps QBX_CAT(QLA, QLB, QLC, QLD);
 const ClassOps QBX_CAT(QLA, QLB, QLC, QLD) = {QLA, QLB, QLC, QLD,
                                               EriClass<QLA, QLB, QLC, QLD>::NCOMP,
-                                              launch_eri, launch_digest, launch_scatter,
+                                              launch_eri, launch_digest, launch_scatter, launch_digest_rows,
                                               (QLA == QLC && QLB == QLD && NCSUM(QLA, QLA + QLB) * NCSUM(QLC, QLC + QLD) < QBX_COOP_ACC)
                                                   ? launch_eri_split : nullptr};

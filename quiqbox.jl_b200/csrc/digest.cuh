@@ -69,19 +69,28 @@ __device__ __forceinline__ void seg_runs(int key0, int key1, int lane, int seg, 
 // per run of lanes that share the bra pair and C (segmented shuffle reduction, one RED per run),
 // K[x d] is consecutive over the lanes.
 template <int NCc, int ND>
-__device__ __forceinline__ void digest_flush_row(double *Kt, int N, int ix, int ic, int id, const double *kxc,
+__device__ __forceinline__ void digest_flush_row(double *Krow, int ic, int id, const double *kxc,
                                                  const double *kxd, double f, bool headC, int endC, bool valid, int lane)
 {
 #pragma unroll
     for (int c = 0; c < NCc; ++c) {
         const double x = seg_sum(f * kxc[c], endC, lane);
-        if (headC && x != 0.0) atomicAdd(Kt + (ic + c) + N * ix, x);
+        if (headC && x != 0.0) atomicAdd(Krow + ic + c, x);
     }
     if (valid) {
 #pragma unroll
-        for (int d = 0; d < ND; ++d) atomicAdd(Kt + (id + d) + N * ix, f * kxd[d]);
+        for (int d = 0; d < ND; ++d) atomicAdd(Krow + id + d, f * kxd[d]);
     }
 }
+
+// Where the rows of the bra functions live.  Default (ROWS = false): in the global density / half-Fock
+// matrices.  ROWS = true (digest_rows_kernel below): the block keeps the exchange-density rows of the
+// current bra pair's functions and their K rows in shared memory.
+struct DigestRows {
+    const double *dA, *dB;       // DK rows of the functions of shell A / B: row x at d?[N * x + column]
+    double *kA, *kB;             // K rows likewise
+    double *jab;                 // J[ab] accumulators, element (a, b) at jab[NB * a + b]
+};
 
 // Kernel structure (ncu, profiles/r01: nothing is saturated, the kernel waits on memory):
 //   * the values of a quartet do not depend on its task record, so the first slab of value loads
@@ -103,9 +112,9 @@ __host__ __device__ constexpr int digest_min_blocks(int ncomp)
 }
 
 // J/K updates of one quartet per lane.  v holds slab 0 of the quartet's values on entry.
-template <int LA, int LB, int LC, int LD, int SL, bool PV>
+template <int LA, int LB, int LC, int LD, int SL, bool PV, bool ROWS = false>
 __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double *__restrict__ vq, bool valid, int2 t, int4 rb,
-                                               int4 rk, double (&v)[SL * NC(LC) * NC(LD)])
+                                               int4 rk, double (&v)[SL * NC(LC) * NC(LD)], const DigestRows &R = DigestRows())
 {
     constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NCD = NCc * ND;
     constexpr bool KEEP_B = NB * (NCc + ND) <= QBX_DIGEST_KEEP_B;     // K[bc], K[bd] live across a
@@ -118,15 +127,22 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
     const int lane = threadIdx.x & 31;
     bool headAB, headC;
     int endAB, endC;
-    seg_runs(t.x, 0, lane, p.seg, headAB, endAB);                   // runs of one bra pair: J[ab]
-    seg_runs(t.x, rk.x, lane, p.seg, headC, endC);                  // runs of one bra pair and one shell C: K[ac], K[bc]
+    // (ROWS: lanes whose quartet belongs to another bra pair take part in the shuffles with f = 0; they get
+    //  a key of their own so that no run mixes them with the active lanes)
+    const int kab = (ROWS && !valid) ? -1 - lane : t.x;
+    seg_runs(kab, 0, lane, p.seg, headAB, endAB);                   // runs of one bra pair: J[ab]
+    seg_runs(kab, rk.x, lane, p.seg, headC, endC);                  // runs of one bra pair and one shell C: K[ac], K[bc]
     const int N = p.nbf;                                      // internal dimension
     const int ia = rb.z, ib = rb.w, ic = rk.z, id = rk.w;
     const double *__restrict__ DJ = p.DJ;
 
-    for (int m = 0; m < p.nmat; ++m) {
-        const double *__restrict__ DK = p.DK + (int64_t)m * N * N;
-        double *Kt = p.Kt + (int64_t)m * N * N;
+    for (int m = 0; m < (ROWS ? 1 : p.nmat); ++m) {
+        const double *__restrict__ dA = ROWS ? R.dA : p.DK + (int64_t)m * N * N + (int64_t)N * ia;
+        const double *__restrict__ dB = ROWS ? R.dB : p.DK + (int64_t)m * N * N + (int64_t)N * ib;
+        double *kA = ROWS ? R.kA : p.Kt + (int64_t)m * N * N + (int64_t)N * ia;
+        double *kB = ROWS ? R.kB : p.Kt + (int64_t)m * N * N + (int64_t)N * ib;
+        double *jab = ROWS ? R.jab : p.Jt + ib + (int64_t)N * ia;
+        const int jsa = ROWS ? NB : N;
         const bool coul = (m == 0);
         double dcd[KEEP_DCD ? NCD : 1], jcd[NCD];
         double dbc[KEEP_B ? NB * NCc : NCc], dbd[KEEP_B ? NB * ND : ND], kbc[KEEP_B ? NB * NCc : NCc], kbd[KEEP_B ? NB * ND : ND];
@@ -142,18 +158,18 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
 #pragma unroll
-                for (int c = 0; c < NCc; ++c) { dbc[b * NCc + c] = DK[(ic + c) + N * (ib + b)]; kbc[b * NCc + c] = 0.0; }
+                for (int c = 0; c < NCc; ++c) { dbc[b * NCc + c] = dB[(ic + c) + N * b]; kbc[b * NCc + c] = 0.0; }
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { dbd[b * ND + d] = DK[(id + d) + N * (ib + b)]; kbd[b * ND + d] = 0.0; }
+                for (int d = 0; d < ND; ++d) { dbd[b * ND + d] = dB[(id + d) + N * b]; kbd[b * ND + d] = 0.0; }
             }
         }
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
             double dac[NCc], dad[ND], kac[NCc], kad[ND];
 #pragma unroll
-            for (int c = 0; c < NCc; ++c) { dac[c] = DK[(ic + c) + N * (ia + a)]; kac[c] = 0.0; }
+            for (int c = 0; c < NCc; ++c) { dac[c] = dA[(ic + c) + N * a]; kac[c] = 0.0; }
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { dad[d] = DK[(id + d) + N * (ia + a)]; kad[d] = 0.0; }
+            for (int d = 0; d < ND; ++d) { dad[d] = dA[(id + d) + N * a]; kad[d] = 0.0; }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const int ab = a * NB + b, s0 = (ab % SL) * NCD;
@@ -164,9 +180,9 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
                 const int ob = KEEP_B ? b : 0;
                 if (!KEEP_B) {
 #pragma unroll
-                    for (int c = 0; c < NCc; ++c) { dbc[c] = DK[(ic + c) + N * (ib + b)]; kbc[c] = 0.0; }
+                    for (int c = 0; c < NCc; ++c) { dbc[c] = dB[(ic + c) + N * b]; kbc[c] = 0.0; }
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) { dbd[d] = DK[(id + d) + N * (ib + b)]; kbd[d] = 0.0; }
+                    for (int d = 0; d < ND; ++d) { dbd[d] = dB[(id + d) + N * b]; kbd[d] = 0.0; }
                 }
                 const double dab = coul ? DJ[(ib + b) + N * (ia + a)] : 0.0;
                 double j = 0.0;
@@ -185,16 +201,16 @@ __device__ __forceinline__ void digest_quartet(const DigestArgs &p, const double
                     }
                 if (coul) {                                   // J[ab]: one address per warp
                     j = seg_sum(j * 2.0 * f, endAB, lane);
-                    if (headAB && j != 0.0) atomicAdd(p.Jt + (ib + b) + N * (ia + a), j);
+                    if (headAB && j != 0.0) atomicAdd(jab + b + jsa * a, j);
                 }
-                if (!KEEP_B) digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc, kbd, f, headC, endC, valid, lane);
+                if (!KEEP_B) digest_flush_row<NCc, ND>(kB + N * b, ic, id, kbc, kbd, f, headC, endC, valid, lane);
             }
-            digest_flush_row<NCc, ND>(Kt, N, ia + a, ic, id, kac, kad, f, headC, endC, valid, lane);
+            digest_flush_row<NCc, ND>(kA + N * a, ic, id, kac, kad, f, headC, endC, valid, lane);
         }
         if (KEEP_B) {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
-                digest_flush_row<NCc, ND>(Kt, N, ib + b, ic, id, kbc + b * NCc, kbd + b * ND, f, headC, endC, valid, lane);
+                digest_flush_row<NCc, ND>(kB + N * b, ic, id, kbc + b * NCc, kbd + b * ND, f, headC, endC, valid, lane);
         }
         if (coul && valid) {                                  // J[cd]: consecutive over the lanes
 #pragma unroll
@@ -235,6 +251,87 @@ __global__ void __launch_bounds__(128, digest_min_blocks(NC(LA) * NC(LB) * NC(LC
     if (t.y < 0) t.y = 0;
     const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);   // (shell A, shell B, first A, first B)
     digest_quartet<LA, LB, LC, LD, SL, true>(p, vq, valid, t, rb, rk, v);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Row-resident digestion (opt-in: QBX_DIGEST_ROWS=1, RHF builds; written without GPU access, to be
+// measured against digest_kernel).  All four exchange updates of a quartet (ab|cd) land in the K rows
+// of its BRA functions, and they read the density rows of its bra functions; tasks are bra-major, so
+// a block that walks a contiguous span of the list stays on one bra pair for hundreds of quartets.
+// It keeps that pair's rows in shared memory:
+//     dA[NA][N], dB[NB][N]   exchange-density rows (loaded once per bra pair, coalesced)
+//     kA[NA][N], kB[NB][N]   K accumulators (shared-memory atomics; flushed once per bra pair with
+//                            coalesced REDs of the non-zero entries), jab[NA][NB] likewise
+// so that per value only D[cd] is gathered from and J[cd] is sent to the global matrices: 2 global
+// accesses per quartet component instead of 12.  A 128-task tile that touches more than two bra
+// pairs (short rows of weakly overlapping pairs) is digested the plain way -- reloading rows for a
+// handful of quartets would cost more than it saves.
+#define QBX_ROWS_MAX_SMEM (200 * 1024)
+
+template <int LA, int LB>
+__host__ __device__ constexpr int digest_rows_doubles(int N) { return 2 * (NC(LA) + NC(LB)) * N + NC(LA) * NC(LB); }
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(128, digest_min_blocks(NC(LA) * NC(LB) * NC(LC) * NC(LD))) digest_rows_kernel(DigestArgs p)
+{
+    constexpr int NA = NC(LA), NB = NC(LB), NCD = NC(LC) * NC(LD), NAB = NA * NB;
+    constexpr int SL = (NAB * NCD <= QBX_DIGEST_SLAB) ? NAB : ((NB * NCD <= QBX_DIGEST_SLAB) ? NB : 1);
+    extern __shared__ double rows_smem[];
+    const int N = p.nbf;
+    DigestRows R;
+    double *sdA = rows_smem, *sdB = sdA + NA * N;
+    R.dA = sdA; R.dB = sdB; R.kA = sdB + NB * N; R.kB = R.kA + NA * N; R.jab = R.kB + NB * N;
+    const int64_t span = p.span;                               // tasks per block, a multiple of 128
+    const unsigned nblk = (unsigned)((p.ntasks + span - 1) / span);
+    const unsigned Rr = nblk < (unsigned)p.spread ? nblk : (unsigned)p.spread, Cc = (nblk + Rr - 1) / Rr;
+    const unsigned blk = (blockIdx.x % Rr) * Cc + blockIdx.x / Rr;     // resident blocks on different bra rows (see digest_kernel)
+    if (blk >= nblk) return;
+    const int64_t s0 = (int64_t)blk * span, s1 = s0 + span < p.ntasks ? s0 + span : p.ntasks;
+    int cur = -1, cia = 0, cib = 0;                            // bra pair whose rows are resident, its first functions
+
+    auto flush = [&]() {                                       // block-wide; callers put barriers around it
+        if (cur < 0) return;
+        for (int i = threadIdx.x; i < NA * N; i += 128) { const double x = R.kA[i]; if (x != 0.0) atomicAdd(p.Kt + (int64_t)N * cia + i, x); }
+        for (int i = threadIdx.x; i < NB * N; i += 128) { const double x = R.kB[i]; if (x != 0.0) atomicAdd(p.Kt + (int64_t)N * cib + i, x); }
+        for (int i = threadIdx.x; i < NAB; i += 128) { const double x = R.jab[i]; if (x != 0.0) atomicAdd(p.Jt + (cib + i % NB) + (int64_t)N * (cia + i / NB), x); }
+    };
+
+    for (int64_t tile = s0; tile < s1; tile += 128) {
+        const int64_t q0 = tile + threadIdx.x;
+        const int64_t q = q0 < s1 ? q0 : s1 - 1;
+        const double *__restrict__ vq = p.vals + q;
+        double v[SL * NCD];
+#pragma unroll
+        for (int i = 0; i < SL * NCD; ++i) v[i] = __ldg(vq + (int64_t)i * p.ntasks);
+        int2 t = __ldg(p.tasks + q);
+        const bool valid = q0 < s1 && t.y >= 0;
+        if (t.y < 0) t.y = 0;
+        const int4 rb = __ldg(p.bra_info + t.x), rk = __ldg(p.ket_info + t.y);
+        const int first = __ldg(p.tasks + tile).x, last = __ldg(p.tasks + (tile + 128 < s1 ? tile + 127 : s1 - 1)).x;   // block-uniform
+        if (last - first > 1) {                                // three or more bra pairs in this tile: plain digestion
+            digest_quartet<LA, LB, LC, LD, SL, true, false>(p, vq, valid, t, rb, rk, v);
+            continue;
+        }
+        for (int target = first; target <= last; ++target) {
+            if (target != cur) {
+                __syncthreads();                               // every warp is done with the resident rows
+                flush();
+                __syncthreads();
+                const int4 tb = __ldg(p.bra_info + target);
+                cur = target; cia = tb.z; cib = tb.w;
+                for (int i = threadIdx.x; i < NA * N; i += 128) { sdA[i] = __ldg(p.DK + (int64_t)N * cia + i); R.kA[i] = 0.0; }
+                for (int i = threadIdx.x; i < NB * N; i += 128) { sdB[i] = __ldg(p.DK + (int64_t)N * cib + i); R.kB[i] = 0.0; }
+                for (int i = threadIdx.x; i < NAB; i += 128) R.jab[i] = 0.0;
+                __syncthreads();
+            }
+            // the second round re-loads slab 0 unless the whole quartet fits in one slab (PV = false)
+            if (SL == NAB || target == first) digest_quartet<LA, LB, LC, LD, SL, true, true>(p, vq, valid && t.x == target, t, rb, rk, v, R);
+            else digest_quartet<LA, LB, LC, LD, SL, false, true>(p, vq, valid && t.x == target, t, rb, rk, v, R);
+        }
+    }
+    __syncthreads();
+    flush();
 }
 
 template <int LA, int LB, int LC, int LD>

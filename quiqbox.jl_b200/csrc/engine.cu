@@ -973,11 +973,15 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             a.spread = spread > 0 ? spread : 1;
             static const int seg = getenv("QBX_DIGEST_SEG") ? atoi(getenv("QBX_DIGEST_SEG")) : 1;
             a.seg = seg;
+            a.span = 128;
+            static const int rows = getenv("QBX_DIGEST_ROWS") ? atoi(getenv("QBX_DIGEST_ROWS")) : 0;     // opt-in, unmeasured
             a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
-                int rc = ops->digest(a, side_[kside++ % kSide]);
+                cudaStream_t ds = side_[kside++ % kSide];
+                int rc = rows ? ops->digest_rows(a, ds) : -1;
+                if (rc < 0) rc = ops->digest(a, ds);
                 if (rc) return rc;
                 stats[0] += 1;
                 stats[5] += (double)tl.n * ops->ncomp * sizeof(double);
@@ -988,7 +992,9 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
                     int rc = run_eri(bc, kc, tl.tasks + o, n, chunk_, s);
                     if (rc) return rc;
                     a.tasks = tl.tasks + o; a.ntasks = n; a.vals = chunk_;
-                    if ((rc = ops->digest(a, s))) return rc;
+                    rc = rows ? ops->digest_rows(a, s) : -1;
+                    if (rc < 0) rc = ops->digest(a, s);
+                    if (rc) return rc;
                     stats[0] += 2;
                 }
                 stats[3] += tl.nprimq;

@@ -25,6 +25,7 @@ struct DigestArgs {
     const double *vals;          // [ncomp][ntasks]
     int nbf, nmat, same_class;   // nbf = internal dimension here
     int spread;                  // number of block slots the task list is dealt over (see digest.cuh)
+    int span;                    // digest_rows_kernel: tasks per block (a multiple of 128)
     int seg;                     // 1: segmented warp reductions (default); 0: per-lane REDs when a warp is not uniform (QBX_DIGEST_SEG, A/B switch)
     const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
@@ -44,6 +45,7 @@ struct ClassOps {
     int (*eri)(const ClassArgs &, cudaStream_t);
     int (*digest)(const DigestArgs &, cudaStream_t);
     int (*scatter)(const ScatterArgs &, cudaStream_t);
+    int (*digest_rows)(const DigestArgs &, cudaStream_t);  // row-resident digestion (QBX_DIGEST_ROWS=1); returns -1 when it does not apply
     int (*eri_split)(const ClassArgs &, cudaStream_t);     // one warp per task (diagonal classes only, else null)
 };
 const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
