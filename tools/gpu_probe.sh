@@ -47,6 +47,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 1 --no-e2e --cpu-seconds 0.2 > "$OUT/ncu_launches.log" 2>&1
 echo "== ncu --set full: digestion, group and cooperative kernels of one store + Fock build"
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    --kernel-name regex:"digest_kernel|eri_group_kernel|eri_coop" --launch-skip 47 --launch-count 47 \
+    --kernel-name regex:"digest_kernel|eri_group_kernel|eri_coop" --launch-skip 30 --launch-count 30 \
     -o "$OUT/full_r02" python tools/e2e_probe.py 2 > "$OUT/ncu_full.log" 2>&1
 ls -la "$OUT"
