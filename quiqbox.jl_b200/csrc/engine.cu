@@ -655,7 +655,10 @@ int Engine::ensure_schwarz(cudaStream_t s)
         if (split && ops->eri_split) {
             ClassArgs a;
             if ((rc = eri_args(pc, pc, t, P.npair, v, cs, a))) return rc;
-            if ((rc = ops->eri_split(a, cs))) return rc;
+            if ((rc = ops->eri_split(a, cs))) {        // e.g. a launch failure: the thread-per-pair kernel still works
+                fprintf(stderr, "[qbx] warp-per-pair Schwarz kernel failed (%s); using one thread per pair\n", qbx_last_error());
+                if ((rc = run_eri(pc, pc, t, P.npair, v, cs))) return rc;
+            }
         } else if ((rc = run_eri(pc, pc, t, P.npair, v, cs))) return rc;
         const int nab = qbx_nc(P.la) * qbx_nc(P.lb);
         k_schwarz<<<(P.npair + 127) / 128, 128, 0, cs>>>(v, P.npair, nab, P.schwarz);

@@ -643,7 +643,12 @@ int launch_coop2(const CoopArgs &c, int64_t ntasks, cudaStream_t s)
     if (trace) fprintf(stderr, "[qbx] coop2 (%d%d|%d%d): %lld quartets, %zu B shared per block, %d blocks/SM\n", LA, LB, LC, LD,
                        (long long)ntasks, smem, per_sm);
     eri_coop2_kernel<LA, LB, LC, LD><<<(unsigned)std::min(need, cap), COOP_WARPS * 32, smem, s>>>(c);
-    QBX_CUDA(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {                      // a launch-configuration error is reported synchronously: nothing ran
+        fprintf(stderr, "[qbx] eri_coop2_kernel<%d,%d,%d,%d> could not be launched (%s); using the table-driven kernel\n", LA, LB, LC,
+                LD, cudaGetErrorString(le));
+        return -2;
+    }
     return QBX_OK;
 }
 
@@ -694,9 +699,13 @@ int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cuda
     for (int i = 0; i < c.nhrr; ++i) c.hrr[i] = P->hrr[i];
     c.acc = P->acc;
     for (int k = 0; k < QBX_BOYS_DEG; ++k) c.boys_inv[k] = 1.0 / (2.0 * (P->L + k) + 1.0);
-    static const int use2 = getenv("QBX_COOP2") ? atoi(getenv("QBX_COOP2")) : 1;
+    static int use2 = getenv("QBX_COOP2") ? atoi(getenv("QBX_COOP2")) : 1;
     if (use2) {
-        if (Coop2Launch f = coop2_for(la, lb, lc, ld)) return f(c, a.ntasks, s);
+        if (Coop2Launch f = coop2_for(la, lb, lc, ld)) {
+            const int rc2 = f(c, a.ntasks, s);
+            if (rc2 != -2) return rc2;
+            use2 = 0;                             // launch failure: stay on the first-generation kernel
+        }
     }
     const size_t smem = (size_t)COOP_WARPS * P->buf_doubles * sizeof(double);
     static bool attr_set = false;
