@@ -402,7 +402,7 @@ Engine *Engine::from_shells(const std::vector<HostShell> &shells, int64_t nbf, b
 }
 
 static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::vector<std::pair<int, int>> sp,
-                         bool sort_by_nprim, DevPairSet &out)
+                         bool sort_by_nprim, DevPairSet &out, std::vector<int2> &shells)
 {
     std::unique_ptr<TraceScope> tr(new TraceScope("pairset: host"));
     // primitive-pair records (zeta, P, K, b, 1/2zeta, 1/zeta); pairs are independent -> host threads
@@ -441,7 +441,7 @@ static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::
     std::iota(order.begin(), order.end(), 0);
     if (sort_by_nprim)
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
-    std::vector<int2> shells(np_);
+    shells.assign(np_, make_int2(0, 0));               // (A, B) per pair in device order, also returned to the caller
     std::vector<int> poff(np_ + 1, 0);
     out.h_nprim.resize(np_);
     for (size_t n = 0; n < np_; ++n) { out.h_nprim[n] = cnt[order[n]]; poff[n + 1] = poff[n] + cnt[order[n]]; }
@@ -531,12 +531,11 @@ int Engine::upload(bool pair_adjacent)
     for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
         // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
         // equal-count group a run of pairs shares A and walks over consecutive B
-        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc]);
+        std::vector<int2> sh;
+        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh);
         if (rc) return rc;
         {
             DevPairSet &P = pairs_[pc];
-            std::vector<int2> sh(P.npair);
-            if (P.npair) QBX_CUDA(cudaMemcpy(sh.data(), P.shells, P.npair * sizeof(int2), cudaMemcpyDeviceToHost));
             std::vector<int4> info(P.npair);
             for (int i = 0; i < P.npair; ++i) info[i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
             QBX_CUDA(qbx_dmalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
