@@ -36,8 +36,14 @@ def emulated_library():
 def test_emulated_library_is_not_the_product_binding():
     from quiqbox_b200 import lib
     assert lib.LIB_PATH.endswith("libqbx.so") and "cuemu" not in lib.LIB_PATH
-    src = open(os.path.join(os.path.dirname(HERE), "quiqbox.jl_b200", "lib.py")).read()
-    assert "emu" not in src.lower().replace("enumerate", "")
+    pkg = os.path.join(os.path.dirname(HERE), "quiqbox.jl_b200")
+    for root, _, files in os.walk(pkg):                       # nothing in the product knows about the emulation
+        if os.path.basename(root) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read().lower()
+                assert "cuemu" not in src and "emu.install" not in src and "libqbx_emu" not in src, f
 
 
 def test_boys_kernels():
