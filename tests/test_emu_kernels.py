@@ -197,3 +197,23 @@ def test_deadlock_detector_reports_divergent_barrier(tmp_path):
                            os.path.join(cu, "cuemu_rt.cpp"), "-o", str(exe), "-pthread"])
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "DEADLOCK" in r.stderr
+
+
+@pytest.mark.parametrize("order", ["forward", "reverse"])
+def test_emulator_warp_semantics(tmp_path, order):
+    """The shim's __shfl*_sync / __ballot_sync / __all_sync / exited-lane / __syncthreads behaviour against what
+    CUDA documents (tests/cuemu_unit/warp_semantics.cpp): a green emulated parity test is only worth as much
+    as the emulation."""
+    import importlib.util
+    root = os.path.dirname(HERE)
+    cu = os.path.join(root, "tools", "cuemu")
+    spec = importlib.util.spec_from_file_location("qbx_build_emu_t", os.path.join(cu, "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    src = tmp_path / "ws.cpp"
+    src.write_text(mod.transform(open(os.path.join(HERE, "cuemu_unit", "warp_semantics.cpp")).read()))
+    exe = tmp_path / "ws"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-fpermissive", "-I", os.path.join(cu, "include"), str(src),
+                           os.path.join(cu, "cuemu_rt.cpp"), "-o", str(exe), "-pthread"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, env=dict(os.environ, QBX_EMU_LANE_ORDER=order))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
