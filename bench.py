@@ -350,7 +350,7 @@ def main():
         except Exception:
             pass
         switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_COOP2", "QBX_COOP_MIN_ACC", "QBX_DIGEST_SEG", "QBX_DIGEST_SPREAD",
-                                               "QBX_DIGEST_ROWS", "QBX_SCHWARZ_SPLIT", "QBX_POOL_GB") if k in os.environ}
+                                               "QBX_DIGEST_ROWS", "QBX_DEVICE_PAIRS", "QBX_SCHWARZ_SPLIT", "QBX_POOL_GB") if k in os.environ}
         per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
                       "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],
                       "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0, "kernel": kernel_name(int(r[0]))} for r in cls if r[2] > 0]

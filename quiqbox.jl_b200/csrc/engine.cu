@@ -126,6 +126,63 @@ __global__ void k_schwarz(const double *vals, int n, int nab, double *Q)
     Q[i] = sqrt(m);
 }
 
+
+// ---- primitive-pair records built on the device (opt-in: QBX_DEVICE_PAIRS=1; written without GPU access).
+// build_pairset() below computes the 64-byte records of ~1.5e5 primitive pairs on host threads and
+// uploads ~25 MB per basis: 6 of the 7 ms of qbx_basis_create for (H2O)16.  Here the host uploads the shell
+// table once (a few kB), a kernel counts the surviving primitive pairs of every shell pair, the host sorts
+// the pairs by that count (the one small read-back), and a second kernel writes the AoS / SoA records in place.
+struct DevShells { const double *cen; const int *xoff; const double *xpn, *coef; };
+
+__device__ __forceinline__ double pair_prefactor(double pref, double a, double b, double ca, double cb, double ab2, double z)
+{
+    return pref * ca * cb * exp(-a * b / z * ab2) / z;        // same expression as the host path (build_pairset)
+}
+
+__global__ void k_pair_count(DevShells S, const int2 *sp, int np, double pref, int *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const int A = sp[i].x, B = sp[i].y;
+    double ab2 = 0;
+    for (int d = 0; d < 3; ++d) { const double t = S.cen[3 * A + d] - S.cen[3 * B + d]; ab2 += t * t; }
+    int c = 0;
+    for (int pa = S.xoff[A]; pa < S.xoff[A + 1]; ++pa)
+        for (int pb = S.xoff[B]; pb < S.xoff[B + 1]; ++pb) {
+            const double a = S.xpn[pa], b = S.xpn[pb];
+            if (fabs(pair_prefactor(pref, a, b, S.coef[pa], S.coef[pb], ab2, a + b)) >= 1e-24) ++c;
+        }
+    cnt[i] = c;
+}
+
+__global__ void k_pair_fill(DevShells S, const int2 *sp, int np, double pref, const int *poff, const int2 *soa_idx, double *prim,
+                            double *soa, double *geom)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= np) return;
+    const int A = sp[n].x, B = sp[n].y;
+    double ab2 = 0, ca[3], cb[3];
+    for (int d = 0; d < 3; ++d) { ca[d] = S.cen[3 * A + d]; cb[d] = S.cen[3 * B + d]; const double t = ca[d] - cb[d]; ab2 += t * t; }
+    for (int d = 0; d < 3; ++d) { geom[8 * (int64_t)n + d] = ca[d]; geom[8 * (int64_t)n + 3 + d] = ca[d] - cb[d]; }
+    geom[8 * (int64_t)n + 6] = geom[8 * (int64_t)n + 7] = 0.0;
+    const int64_t b0 = soa_idx[n].x, g = soa_idx[n].y;
+    int c = 0;
+    for (int pa = S.xoff[A]; pa < S.xoff[A + 1]; ++pa)
+        for (int pb = S.xoff[B]; pb < S.xoff[B + 1]; ++pb) {
+            const double a = S.xpn[pa], b = S.xpn[pb], z = a + b;
+            const double K = pair_prefactor(pref, a, b, S.coef[pa], S.coef[pb], ab2, z);
+            if (fabs(K) < 1e-24) continue;
+            double v[8];
+            v[0] = z;
+            for (int d = 0; d < 3; ++d) v[1 + d] = (a * ca[d] + b * cb[d]) / z;
+            v[4] = K; v[5] = b; v[6] = 0.5 / z; v[7] = 1.0 / z;
+            double *r = prim + 8 * ((int64_t)poff[n] + c);
+            for (int k = 0; k < 8; ++k) r[k] = v[k];
+            for (int k = 0; k < QBX_SOA_NF; ++k) soa[b0 + ((int64_t)c * QBX_SOA_NF + k) * g] = v[k];
+            ++c;
+        }
+}
+
 // one warp per bra row
 __global__ void k_count_tasks(const double *Qb, const double *Qk, int nb, int nk, int same, double tol, int *cnt)
 {
@@ -494,6 +551,74 @@ static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::
     return QBX_OK;
 }
 
+
+// device variant of build_pairset (see k_pair_count / k_pair_fill); same outputs
+static int build_pairset_device(const std::vector<HostShell> &sh, const DevShells &S, int la, int lb,
+                                const std::vector<std::pair<int, int>> &sp, bool sort_by_nprim, DevPairSet &out,
+                                std::vector<int2> &shells, cudaStream_t s)
+{
+    (void)sh;
+    const size_t np_ = sp.size();
+    out.la = la; out.lb = lb; out.npair = (int)np_; out.nprim = 0;
+    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
+    std::vector<int2> sp0(np_);
+    for (size_t i = 0; i < np_; ++i) sp0[i] = make_int2(sp[i].first, sp[i].second);
+    std::vector<int> cnt(np_, 0);
+    int2 *d_sp = nullptr; int *d_cnt = nullptr;
+    QBX_CUDA(qbx_dmalloc(&d_sp, std::max<size_t>(1, np_) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&d_cnt, std::max<size_t>(1, np_) * sizeof(int)));
+    if (np_) {
+        QBX_CUDA(cudaMemcpyAsync(d_sp, sp0.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        k_pair_count<<<(unsigned)((np_ + 127) / 128), 128, 0, s>>>(S, d_sp, (int)np_, pref, d_cnt);
+        QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, np_ * sizeof(int), cudaMemcpyDeviceToHost, s));
+        QBX_CUDA(cudaStreamSynchronize(s));                  // the one read-back: primitive pairs per shell pair
+    }
+    std::vector<int> order(np_);
+    std::iota(order.begin(), order.end(), 0);
+    if (sort_by_nprim)
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+    shells.assign(np_, make_int2(0, 0));
+    std::vector<int> poff(np_ + 1, 0);
+    out.h_nprim.resize(np_);
+    for (size_t n = 0; n < np_; ++n) {
+        shells[n] = sp0[order[n]];
+        out.h_nprim[n] = cnt[order[n]];
+        poff[n + 1] = poff[n] + cnt[order[n]];
+    }
+    out.nprim = poff[np_];
+    const size_t n_prim = 8 * (size_t)poff[np_], n_soa = (size_t)QBX_SOA_NF * poff[np_];
+    std::vector<int2> soa_idx(np_);
+    {
+        size_t base = 0, g0 = 0;
+        while (g0 < np_) {
+            size_t g1 = g0;
+            while (g1 < np_ && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
+            const size_t g = g1 - g0;
+            for (size_t j = g0; j < g1; ++j) soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
+            base += g * (size_t)out.h_nprim[g0] * QBX_SOA_NF;
+            g0 = g1;
+        }
+    }
+    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, np_) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&out.shells, std::max<size_t>(1, np_) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, 8 * np_) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, n_prim) * sizeof(double)));
+    QBX_CUDA(qbx_dmalloc(&out.schwarz, std::max<size_t>(1, np_) * sizeof(double)));
+    QBX_CUDA(cudaMemcpyAsync(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (np_) {
+        QBX_CUDA(cudaMemcpyAsync(out.soa_idx, soa_idx.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaMemcpyAsync(out.shells, shells.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        k_pair_fill<<<(unsigned)((np_ + 127) / 128), 128, 0, s>>>(S, out.shells, (int)np_, pref, out.prim_off, out.soa_idx, out.prim,
+                                                                  out.soa, out.geom);
+        QBX_CUDA(cudaGetLastError());
+    }
+    QBX_CUDA(cudaStreamSynchronize(s));                      // the host vectors above go out of scope
+    qbx_pool_free_async(d_sp); qbx_pool_free_async(d_cnt);
+    return QBX_OK;
+}
+
 int Engine::upload(bool pair_adjacent)
 {
     const size_t ns = shells_.size();
@@ -528,11 +653,33 @@ int Engine::upload(bool pair_adjacent)
     }
     std::vector<int> first_h(ns);
     { int acc = 0; for (size_t s = 0; s < ns; ++s) { first_h[s] = acc; acc += qbx_nc(shells_[s].l); } }
+    // QBX_DEVICE_PAIRS=1: primitive-pair records computed on the device (opt-in, unmeasured)
+    static const int dev_pairs = getenv("QBX_DEVICE_PAIRS") ? atoi(getenv("QBX_DEVICE_PAIRS")) : 0;
+    DevShells S{nullptr, nullptr, nullptr, nullptr};
+    void *d_tab[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (dev_pairs) {
+        std::vector<double> cen(3 * ns), xp, cf;
+        std::vector<int> xoff(ns + 1, 0);
+        for (size_t i = 0; i < ns; ++i) {
+            for (int d = 0; d < 3; ++d) cen[3 * i + d] = shells_[i].cen[d];
+            xp.insert(xp.end(), shells_[i].xpn.begin(), shells_[i].xpn.end());
+            cf.insert(cf.end(), shells_[i].coef.begin(), shells_[i].coef.end());
+            xoff[i + 1] = (int)xp.size();
+        }
+        const size_t bytes[4] = {cen.size() * sizeof(double), xoff.size() * sizeof(int), xp.size() * sizeof(double), cf.size() * sizeof(double)};
+        const void *src[4] = {cen.data(), xoff.data(), xp.data(), cf.data()};
+        for (int i = 0; i < 4; ++i) {
+            QBX_CUDA(qbx_pool_malloc(&d_tab[i], std::max<size_t>(8, bytes[i])));
+            if (bytes[i]) QBX_CUDA(cudaMemcpy(d_tab[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+        }
+        S = DevShells{(const double *)d_tab[0], (const int *)d_tab[1], (const double *)d_tab[2], (const double *)d_tab[3]};
+    }
     for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
         // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
         // equal-count group a run of pairs shares A and walks over consecutive B
         std::vector<int2> sh;
-        int rc = build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh);
+        int rc = dev_pairs ? build_pairset_device(shells_, S, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh, qbx_stream())
+                           : build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh);
         if (rc) return rc;
         {
             DevPairSet &P = pairs_[pc];
@@ -548,6 +695,7 @@ int Engine::upload(bool pair_adjacent)
             }
         }
     }
+    for (void *p : d_tab) qbx_pool_free_async(p);
     QBX_CUDA(cudaEventCreate(&ev0_));
     QBX_CUDA(cudaEventCreate(&ev1_));
     return QBX_OK;

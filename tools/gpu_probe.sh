@@ -21,6 +21,8 @@ timeout 600 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.e
 echo "== e2e A/B: Schwarz diagonals one thread per pair (round-1 behaviour)"
 QBX_SCHWARZ_SPLIT=0 QBX_TRACE=1 timeout 600 python bench.py --steps 3 --warmup 3 --cpu-seconds 0 > "$OUT/bench_schwarz_thread.json" 2> "$OUT/bench_schwarz_thread.err"
 QBX_TRACE=1 timeout 600 python bench.py --steps 3 --warmup 3 --cpu-seconds 0 > "$OUT/bench_schwarz_warp.json" 2> "$OUT/bench_schwarz_warp.err"
+echo "== e2e candidate: primitive-pair records built on the device"
+QBX_DEVICE_PAIRS=1 QBX_TRACE=1 timeout 600 python bench.py --steps 3 --warmup 3 --cpu-seconds 0 > "$OUT/bench_device_pairs.json" 2> "$OUT/bench_device_pairs.err"
 echo "== bench --steps 10 (no e2e, no cpu leg)"
 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10.json" 2> "$OUT/bench_s10.err"
 echo "== digestion A/B: per-lane REDs on non-uniform warps (round-1 behaviour)"
