@@ -690,7 +690,7 @@ int Engine::upload(bool pair_adjacent)
             // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
             if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
                 TraceScope trg("group build");
-                if ((rc = qbx_group_build(shells_, sh, groups_))) return rc;
+                if ((rc = qbx_group_build(shells_, sh, groups_, dev_pairs ? P.shells : nullptr))) return rc;
                 use_groups_ = groups_.ng > 0 && groups_.ng < P.npair;     // only when something is shared
             }
         }

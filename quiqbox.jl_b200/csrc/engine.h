@@ -93,7 +93,8 @@ struct GroupSet {
     int2 *soa_idx = nullptr;
     std::vector<int> h_nprim, h_nmem;
 };
-int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out);
+int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out,
+                    const int2 *d_ss_pairs = nullptr);   // d_ss_pairs != null: records computed on the device (QBX_DEVICE_PAIRS=1)
 void qbx_group_free(GroupSet &g);
 // two enqueue-only phases, see Engine::tasks_count / tasks_fill.  d_total[0..2] = group tasks of all
 // ranks, group tasks of this rank, slots of this rank.

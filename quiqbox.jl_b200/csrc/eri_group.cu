@@ -261,12 +261,83 @@ int launch_group(GroupArgs a, cudaStream_t s)
     return QBX_OK;
 }
 
+
+// ---- group-pair primitive records on the device (QBX_DEVICE_PAIRS=1, see engine.cu: k_pair_count / k_pair_fill)
+struct GroupTables {
+    const double *gcen;          // [npg][3] centre of a primitive group
+    const int *gxoff;            // [npg + 1] exponents of group g at gxpn[gxoff[g] ..]
+    const double *gxpn;
+    const int *scoef_off;        // [nshell + 1]: coefficients of s shell s over its group's primitives
+    const double *scoef;
+    const int *spg;              // [nshell] group of an s shell
+    const int2 *gp;              // [ng] (P, Q)
+    const int *gmem;             // [ng][9] member pair indices (regular (ss) pairs), -1 = none
+    const int2 *ss;              // regular (ss) pairs: shells (C, D)
+};
+
+__device__ __forceinline__ double group_prim(const GroupTables &T, int g, int P, int Q, int a, int b, double pref, double pq2,
+                                             double (&v)[QBX_GRP_NF])
+{
+    const double x = T.gxpn[a], y = T.gxpn[b], z = x + y;
+    v[0] = z;
+    for (int d = 0; d < 3; ++d) v[1 + d] = (x * T.gcen[3 * P + d] + y * T.gcen[3 * Q + d]) / z;
+    v[4] = pref * exp(-x * y / z * pq2) / z;
+    const int pa = a - T.gxoff[P], pb = b - T.gxoff[Q];
+    double big = 0.0;
+    for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
+        double cc = 0.0;
+        const int j = T.gmem[g * QBX_GRP_MAXMEM + m];
+        if (j >= 0) {
+            const int2 cd = T.ss[j];
+            if (T.spg[cd.x] == P) cc = T.scoef[T.scoef_off[cd.x] + pa] * T.scoef[T.scoef_off[cd.y] + pb];
+            else cc = T.scoef[T.scoef_off[cd.y] + pa] * T.scoef[T.scoef_off[cd.x] + pb];
+        }
+        v[5 + m] = cc;
+        big = fmax(big, fabs(cc * v[4]));
+    }
+    return big;
+}
+
+__global__ void k_group_count(GroupTables T, int ng, double pref, int *cnt)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ng) return;
+    const int P = T.gp[g].x, Q = T.gp[g].y;
+    double pq2 = 0;
+    for (int d = 0; d < 3; ++d) { const double t = T.gcen[3 * P + d] - T.gcen[3 * Q + d]; pq2 += t * t; }
+    int c = 0;
+    double v[QBX_GRP_NF];
+    for (int a = T.gxoff[P]; a < T.gxoff[P + 1]; ++a)
+        for (int b = T.gxoff[Q]; b < T.gxoff[Q + 1]; ++b)
+            if (group_prim(T, g, P, Q, a, b, pref, pq2, v) >= 1e-24) ++c;
+    cnt[g] = c;
+}
+
+__global__ void k_group_fill(GroupTables T, int ng, double pref, const int *order, const int2 *soa_idx, double *soa)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ng) return;
+    const int g = order[n];
+    const int P = T.gp[g].x, Q = T.gp[g].y;
+    double pq2 = 0;
+    for (int d = 0; d < 3; ++d) { const double t = T.gcen[3 * P + d] - T.gcen[3 * Q + d]; pq2 += t * t; }
+    const int64_t b0 = soa_idx[n].x, gs = soa_idx[n].y;
+    int c = 0;
+    double v[QBX_GRP_NF];
+    for (int a = T.gxoff[P]; a < T.gxoff[P + 1]; ++a)
+        for (int b = T.gxoff[Q]; b < T.gxoff[Q + 1]; ++b) {
+            if (group_prim(T, g, P, Q, a, b, pref, pq2, v) < 1e-24) continue;
+            for (int k = 0; k < QBX_GRP_NF; ++k) soa[b0 + ((int64_t)c * QBX_GRP_NF + k) * gs] = v[k];
+            ++c;
+        }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ host side
 // Primitive groups of the s shells and the (ss) group pairs.  `ss_pairs` = shells of every
 // regular (ss) pair in the order of the device pair set.
-int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out)
+int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out, const int2 *d_ss_pairs)
 {
     // 1. primitive groups: s shells on one centre whose exponents are a subset of the group's
     struct PG { double cen[3]; std::vector<double> xpn; std::vector<int> shells; };
@@ -317,10 +388,87 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
     const size_t ng0 = members.size();
     for (auto &m : members)
         if (m.size() > QBX_GRP_MAXMEM) { qbx_set_error("internal: group pair with more than 9 members"); return QBX_ERR_STATE; }
+    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
+    if (d_ss_pairs && ng0 > 0) {
+        // ---- device path (QBX_DEVICE_PAIRS=1): count -> host sort by count -> fill
+        cudaStream_t st = qbx_stream();
+        std::vector<double> gcen(3 * pgs.size()), gxpn, scoef;
+        std::vector<int> gxoff(pgs.size() + 1, 0), scoef_off(sh.size() + 1, 0), gmem(ng0 * QBX_GRP_MAXMEM, -1);
+        std::vector<int2> gp(ng0);
+        for (size_t g = 0; g < pgs.size(); ++g) {
+            for (int d = 0; d < 3; ++d) gcen[3 * g + d] = pgs[g].cen[d];
+            gxpn.insert(gxpn.end(), pgs[g].xpn.begin(), pgs[g].xpn.end());
+            gxoff[g + 1] = (int)gxpn.size();
+        }
+        for (size_t i = 0; i < sh.size(); ++i) {
+            scoef.insert(scoef.end(), coef[i].begin(), coef[i].end());
+            scoef_off[i + 1] = (int)scoef.size();
+        }
+        for (size_t g = 0; g < ng0; ++g) {
+            gp[g] = make_int2(gp_pq[g].first, gp_pq[g].second);
+            for (size_t m = 0; m < members[g].size(); ++m) gmem[g * QBX_GRP_MAXMEM + m] = members[g][m];
+        }
+        void *d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const void *src[8] = {gcen.data(), gxoff.data(), gxpn.data(), scoef_off.data(), scoef.data(), pg_of.data(), gp.data(), gmem.data()};
+        const size_t bytes[8] = {gcen.size() * 8, gxoff.size() * 4, gxpn.size() * 8, scoef_off.size() * 4, scoef.size() * 8,
+                                 pg_of.size() * 4, gp.size() * sizeof(int2), gmem.size() * 4};
+        for (int i = 0; i < 8; ++i) {
+            QBX_CUDA(qbx_pool_malloc(&d[i], std::max<size_t>(8, bytes[i])));
+            if (bytes[i]) QBX_CUDA(cudaMemcpyAsync(d[i], src[i], bytes[i], cudaMemcpyHostToDevice, st));
+        }
+        GroupTables T{(const double *)d[0], (const int *)d[1], (const double *)d[2], (const int *)d[3], (const double *)d[4],
+                      (const int *)d[5], (const int2 *)d[6], (const int *)d[7], d_ss_pairs};
+        int *d_cnt = nullptr, *d_order = nullptr;
+        QBX_CUDA(qbx_dmalloc(&d_cnt, ng0 * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&d_order, ng0 * sizeof(int)));
+        std::vector<int> cnt(ng0);
+        k_group_count<<<(unsigned)((ng0 + 127) / 128), 128, 0, st>>>(T, (int)ng0, pref, d_cnt);
+        QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, ng0 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        QBX_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> order(ng0);
+        for (size_t g = 0; g < ng0; ++g) order[g] = (int)g;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+        out.ng = (int)ng0;
+        out.h_nprim.resize(ng0); out.h_nmem.resize(ng0);
+        std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0);
+        for (size_t n = 0; n < ng0; ++n) {
+            const int g = order[n];
+            out.h_nprim[n] = cnt[g];
+            out.h_nmem[n] = (int)members[g].size();
+            for (size_t m = 0; m < members[g].size(); ++m) mem[n * QBX_GRP_MAXMEM + m] = members[g][m];
+            poff[n + 1] = poff[n] + cnt[g];
+        }
+        std::vector<int2> soa_idx(ng0);
+        size_t base = 0, g0 = 0;
+        while (g0 < ng0) {
+            size_t g1 = g0;
+            while (g1 < ng0 && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
+            const size_t gs = g1 - g0;
+            for (size_t n = g0; n < g1; ++n) soa_idx[n] = make_int2((int)(base + (n - g0)), (int)gs);
+            base += gs * (size_t)out.h_nprim[g0] * QBX_GRP_NF;
+            g0 = g1;
+        }
+        const size_t n_soa = (size_t)QBX_GRP_NF * poff.back();
+        QBX_CUDA(qbx_dmalloc(&out.nmem, ng0 * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&out.members, mem.size() * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa) * sizeof(double)));
+        QBX_CUDA(qbx_dmalloc(&out.soa_idx, ng0 * sizeof(int2)));
+        QBX_CUDA(cudaMemcpyAsync(out.nmem, out.h_nmem.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice, st));
+        QBX_CUDA(cudaMemcpyAsync(out.members, mem.data(), mem.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        QBX_CUDA(cudaMemcpyAsync(out.soa_idx, soa_idx.data(), ng0 * sizeof(int2), cudaMemcpyHostToDevice, st));
+        QBX_CUDA(cudaMemcpyAsync(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        QBX_CUDA(cudaMemcpyAsync(d_order, order.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_group_fill<<<(unsigned)((ng0 + 127) / 128), 128, 0, st>>>(T, (int)ng0, pref, d_order, out.soa_idx, out.soa);
+        QBX_CUDA(cudaGetLastError());
+        QBX_CUDA(cudaStreamSynchronize(st));                 // host vectors go out of scope
+        for (void *q : d) qbx_pool_free_async(q);
+        qbx_pool_free_async(d_cnt); qbx_pool_free_async(d_order);
+        return QBX_OK;
+    }
     // 3. primitive pairs of each group pair: geometry + the members' coefficient products
     struct Rec { double v[QBX_GRP_NF]; };
     std::vector<std::vector<Rec>> prims(ng0);
-    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
     qbx_parallel_for(ng0, 32, [&](size_t lo, size_t hi) {
     for (size_t g = lo; g < hi; ++g) {
         const PG &P = pgs[gp_pq[g].first], &Q = pgs[gp_pq[g].second];
