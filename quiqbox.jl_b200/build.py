@@ -38,8 +38,13 @@ def _compile(job):
 
 
 def build(jobs=None, force=False, verbose=True):
-    os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    # a library that is newer than every source is up to date even when the object files are not there
+    # (they do not travel to the GPU box: .gpurunignore)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + hdrs
+    if not force and os.path.exists(LIB) and not _newer(LIB, srcs):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
     work, objs = [], []
     for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool"):
         src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o")

@@ -53,7 +53,7 @@ timeout 1200 ncu --set full --clock-control none --import-source on \
     -o "$OUT/full_r02" python tools/e2e_probe.py 2 > "$OUT/ncu_full.log" 2>&1
 echo "== compute-sanitizer on the smoke test (everything above was developed under CPU emulation only)"
 for tool in memcheck racecheck synccheck; do
-  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python __graft_entry__.py --smoke > "$OUT/sanitizer_$tool.log" 2>&1
+  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python -c 'import __graft_entry__ as g; g.smoke()' > "$OUT/sanitizer_$tool.log" 2>&1
   echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok" "$OUT/sanitizer_$tool.log" | tail -3
 done
 ls -la "$OUT"
