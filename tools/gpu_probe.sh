@@ -44,6 +44,9 @@ for f in sorted(glob.glob("gpurun_out/probe/bench_*.json")):
         print(f, "unreadable:", e)
 PY
 
+echo "== synthetic per-class sweep (both cooperative generations)"
+timeout 900 python tools/sweep_synthetic.py > "$OUT/synthetic_sweep.md" 2> "$OUT/synthetic_sweep.err"
+QBX_COOP2=0 timeout 600 python tools/sweep_synthetic.py > "$OUT/synthetic_sweep_coop1.md" 2>/dev/null
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
     python bench.py --steps 2 --warmup 1 --no-e2e --cpu-seconds 0.2 > "$OUT/ncu_launches.log" 2>&1
