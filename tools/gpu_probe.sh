@@ -3,7 +3,7 @@
 # (segmented digestion reductions, 2-load Boys table, cooperative kernel) and leaves the evidence
 # in gpurun_out/ (copy the summaries you keep into profiles/rNN/):
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_probe.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_probe.sh'
 #
 # Steps: GPU parity tests -> bench default -> digestion A/B (QBX_DIGEST_SEG=0) -> spread sweep ->
 # ncu launch list of the bench command -> ncu --set full of the digestion / group / cooperative kernels.
