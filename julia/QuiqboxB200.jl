@@ -68,6 +68,26 @@ end
 
 eligible(source) = all(f -> f isa FloatingPolyGaussField{Float64, 3}, source)
 
+# Resident mode.  initializeHartreeFock keeps whatever seam 1 returns in ElecHamiltonianConfig.twoBody
+# (`_, eriH = computeOrbDataIntegral(style2B, eriOp, eriBasis)`, HartreeFock.jl:189-193; the result of
+# getOrbVectorIntegralCore! is passed through unchanged, Framework.jl:835-840, 907-916), and that field is
+# typed A4 <: AbstractArray{T,4}.  With RESIDENT[] = true seam 1 therefore returns the device handle
+# (packed unique ERIs in HBM, qbx_eri_store) instead of materialising N^4 doubles on the host, and every
+# later getGcore(HeeI, DJ, DK) of the SCF loop dispatches to qbx_fock_build (seam 2 below):
+#     QuiqboxB200.with_device_eri() do;  runHartreeFock(nucInfo, bs);  end
+const RESIDENT = Ref(false)
+const SCREEN = Ref(1e-12)          # Schwarz threshold of the resident store
+const SHARD = Ref((0, 1))          # (rank, nranks) of this process (one Julia process per GPU)
+function with_device_eri(f; screen::Float64=1e-12, rank::Integer=0, nranks::Integer=1)
+    old = (RESIDENT[], SCREEN[], SHARD[])
+    RESIDENT[], SCREEN[], SHARD[] = true, screen, (Int(rank), Int(nranks))
+    try
+        return f()
+    finally
+        RESIDENT[], SCREEN[], SHARD[] = old
+    end
+end
+
 # ---- seam 1: the whole N^4 tensor (elecRepulsions) ------------------------------------------
 function Quiqbox.getOrbVectorIntegralCore!(
         inteInfo::TwoBodyOrbIntegralInfo{Float64, 3, Float64, <:CoulombInteractionSampler},
@@ -76,6 +96,7 @@ function Quiqbox.getOrbVectorIntegralCore!(
     all(==(PrimGaussTypeOrb), inteInfo.source.right) && eligible(src) ||
         return invoke(Quiqbox.getOrbVectorIntegralCore!,
                       Tuple{Quiqbox.TwoBodyOrbIntegralInfo, Quiqbox.OrbCorePointerVector}, inteInfo, ptrVector)
+    RESIDENT[] && return DeviceERI(src, ptrVector; screen=SCREEN[], rank=SHARD[][1], nranks=SHARD[][2])
     b = flatten(src, ptrVector)
     n = b.nbf
     out = Array{Float64}(undef, n, n, n, n)                     # column-major, tensor[i,j,k,l] = (ij|kl)
