@@ -17,6 +17,9 @@ LIB = os.path.join(HERE, "libqbx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-I", CSRC]
+# tuning constants for A/B builds on the GPU box, e.g. QBX_NVCC_DEFS="-DQBX_ERI_THREADS=128 -DCOOP_WARPS=8"
+# (then --force; the defaults are the product)
+FLAGS += os.environ.get("QBX_NVCC_DEFS", "").split()
 
 CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]

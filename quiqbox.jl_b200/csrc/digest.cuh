@@ -26,7 +26,9 @@
 #pragma once
 #include "engine.h"
 
+#ifndef QBX_DIGEST_SPREAD
 #define QBX_DIGEST_SPREAD 384
+#endif
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -102,8 +104,12 @@ struct DigestRows {
 //   * the block factor f multiplies the sums at flush time, not the values.
 // Values are read once and feed J and K together (the second exchange density of a UHF build
 // re-reads them).
+#ifndef QBX_DIGEST_SLAB
 #define QBX_DIGEST_SLAB 64
+#endif
+#ifndef QBX_DIGEST_KEEP_B
 #define QBX_DIGEST_KEEP_B 18
+#endif
 
 // resident blocks per SM the register allocation aims at (128 threads each)
 __host__ __device__ constexpr int digest_min_blocks(int ncomp)

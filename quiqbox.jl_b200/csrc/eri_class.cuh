@@ -291,7 +291,9 @@ struct EriClass {
     }
 };
 
+#ifndef QBX_ERI_THREADS
 #define QBX_ERI_THREADS 256
+#endif
 
 // Persistent blocks: the Boys columns of this class are staged in shared memory once, then
 // its warps pull chunks of 32 consecutive tasks from a global work queue.  The list is

@@ -261,8 +261,12 @@ __device__ __forceinline__ void boys_rt(const BoysTable &tb, const double *inv_o
     for (int m = L; m >= 1; --m) { f = fma(t2, f, ex) * (1.0 / (2.0 * m - 1.0)); F[m - 1] = f; }
 }
 
+#ifndef COOP_WARPS
 #define COOP_WARPS 4
+#endif
+#ifndef COOP_BATCH
 #define COOP_BATCH 4
+#endif
 
 // op record i of a level, or a harmless self-referencing dummy past the end
 __device__ __forceinline__ Op ld_op(const Op *ops, int i, int n)
