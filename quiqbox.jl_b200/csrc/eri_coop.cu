@@ -437,7 +437,6 @@ template <int LA, int LB, int LC, int LD>
 struct Coop2 {
     static constexpr int E = LA + LB, F = LC + LD, L = E + F;
     static constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NAB = NA * NB;
-    static constexpr int NCOMP = NAB * NCc * ND;
     static constexpr int NACC = NCSUM(LA, E), NKET = NCSUM(LC, F);
     static constexpr int GT = S1(L + 1);                       // all stacked bra components, degrees 0..L
     static constexpr int GB = S1(LA);                          // lane 0 of pass 0 owns the first contracted component
@@ -465,9 +464,8 @@ struct Coop2 {
     static constexpr int NP = NPH + (GB > 0 ? 1 : 0);
     static __host__ __device__ constexpr int pass_lo(int q) { return q < NPH ? GB + 32 * q : 0; }
     static __host__ __device__ constexpr int pass_hi(int q) { return q < NPH ? (GB + 32 * q + 32 < GT ? GB + 32 * q + 32 : GT) : GB; }
-    // passes that hold targets of some transfer level >= 1 (the others only take part in the level-0 copy)
+    // does pass q hold targets of transfer level f?  (decided at compile time: whole passes drop out of a level)
     static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return pass_lo(q) < ghi(f) && pass_hi(q) > glo(f); }
-    static __host__ __device__ constexpr bool pass_has_info(int q) { return pass_in_level(q, 1); }
 
     struct LaneInfo {            // per pass
         int g;                   // own stacked index (or -1: lane idle in this pass)
