@@ -655,7 +655,8 @@ int launch_coop2(const CoopArgs &c, int64_t ntasks, cudaStream_t s)
 }
 
 // classes compiled for the second-generation kernel: everything the thread kernels do not serve, plus
-// the two thread-kernel classes that spill at 255 registers ((dp|pp), (dp|ds))
+// the thread-kernel classes that spill at 255 registers ((dp|pp), (dp|ds), (dd|ps)); those are routed here only when
+// QBX_COOP_MIN_ACC is lowered (A/B runs: by instruction count the thread kernels should still win)
 Coop2Launch coop2_for(int la, int lb, int lc, int ld)
 {
     const int key = la * 1000 + lb * 100 + lc * 10 + ld;
@@ -667,6 +668,7 @@ Coop2Launch coop2_for(int la, int lb, int lc, int ld)
         case 2222: return launch_coop2<2, 2, 2, 2>;
         case 2111: return launch_coop2<2, 1, 1, 1>;
         case 2120: return launch_coop2<2, 1, 2, 0>;
+        case 2210: return launch_coop2<2, 2, 1, 0>;     // reached only with QBX_COOP_MIN_ACC <= 93 (A/B against the thread kernel)
         default: return nullptr;
     }
 }
