@@ -290,38 +290,6 @@ assert err < 1e-12
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def test_cooperative_kernel_generations_agree():
-    """The compiled cooperative kernel (eri_coop2_kernel: lane = stacked bra component, QBX_COOP2=1, default) and
-    the table-driven interpreter (QBX_COOP2=0) execute the same recurrences in the same order: on synthetic
-    batches of every class the former serves their checksums agree to rounding of the final sum."""
-    import subprocess
-    import sys
-    code = r'''
-import sys, ctypes as C
-sys.path[:0] = [%r, %r]
-BOOT
-import numpy as np
-from quiqbox_b200 import lib as L
-L.init()
-for cls in [(2,1,2,1),(2,2,1,1),(2,2,2,0),(2,2,2,1),(2,2,2,2)]:
-    for K in (1, 2):
-        nq = 2048
-        secs, chk, npq = C.c_double(), C.c_double(), C.c_double()
-        L.check(L.load().qbx_prim_batch(*cls, K, nq, 7, C.byref(secs), C.byref(chk), C.byref(npq), 0, None, None))
-        print("CHK %%.17e" %% chk.value)
-''' % (os.path.dirname(HERE), HERE)
-    code = code.replace("BOOT", os.environ.get("QBX_TEST_BOOT", ""))
-    vals = []
-    for gen in ("1", "0"):
-        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, QBX_COOP2=gen), capture_output=True, text=True,
-                           timeout=900)
-        assert r.returncode == 0, r.stdout + r.stderr
-        vals.append([float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("CHK")])
-    assert len(vals[0]) == 10 and len(vals[1]) == 10
-    for a, b in zip(*vals):
-        assert abs(a - b) <= 1e-11 * max(1.0, abs(b)), (a, b)
-
-
 # ------------------------------------------------------------------ BASELINE.json configs [2] and [3]
 def test_benzene_and_water_dimer_scf_vs_oracle_energy():
     g = json.load(open(os.path.join(HERE, "golden", "oracle_energies.json")))
@@ -471,3 +439,36 @@ def test_allocation_pool_reuse_and_trim():
     T = qb.elecRepulsions(bs2)
     Tref = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs2)).eri_tensor()
     assert np.max(np.abs(T - Tref)) < 1e-12
+
+
+# ------------------------------------------------------------------ new in the last commits of round 1 (kept last: pytest -x)
+def test_cooperative_kernel_generations_agree():
+    """The compiled cooperative kernel (eri_coop2_kernel: lane = stacked bra component, QBX_COOP2=1, default) and
+    the table-driven interpreter (QBX_COOP2=0) execute the same recurrences in the same order: on synthetic
+    batches of every class the former serves their checksums agree to rounding of the final sum."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, ctypes as C
+sys.path[:0] = [%r, %r]
+BOOT
+import numpy as np
+from quiqbox_b200 import lib as L
+L.init()
+for cls in [(2,1,2,1),(2,2,1,1),(2,2,2,0),(2,2,2,1),(2,2,2,2)]:
+    for K in (1, 2):
+        nq = 2048
+        secs, chk, npq = C.c_double(), C.c_double(), C.c_double()
+        L.check(L.load().qbx_prim_batch(*cls, K, nq, 7, C.byref(secs), C.byref(chk), C.byref(npq), 0, None, None))
+        print("CHK %%.17e" %% chk.value)
+''' % (os.path.dirname(HERE), HERE)
+    code = code.replace("BOOT", os.environ.get("QBX_TEST_BOOT", ""))
+    vals = []
+    for gen in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, QBX_COOP2=gen), capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        vals.append([float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("CHK")])
+    assert len(vals[0]) == 10 and len(vals[1]) == 10
+    for a, b in zip(*vals):
+        assert abs(a - b) <= 1e-11 * max(1.0, abs(b)), (a, b)
