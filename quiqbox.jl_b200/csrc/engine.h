@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -134,7 +135,12 @@ private:
                    const int64_t *h_total, TaskList &out, double *d_stat, int *d_nheavy, cudaStream_t s);
     int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, const int *order = nullptr);
     int eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a);
-    bool grouped(int bc, int kc) const { return use_groups_ && kc == 0 && (bc == 0 || bc == 1); }   // (ss|ss), (ps|ss); (ds|ss) measured slower
+    // (ss|ss), (ps|ss); (ds|ss) was measured slower with its 54 accumulators (QBX_GC_DS=1 includes it: A/B runs)
+    bool grouped(int bc, int kc) const
+    {
+        static const bool ds = getenv("QBX_GC_DS") && atoi(getenv("QBX_GC_DS"));
+        return use_groups_ && kc == 0 && (bc == 0 || bc == 1 || (ds && bc == 3));
+    }
     GroupSet groups_;
     bool use_groups_ = false;
 
