@@ -349,7 +349,7 @@ def main():
                 traffic = tj["dram_bytes_per_launch"].get(kernel_name(code))
         except Exception:
             pass
-        switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_GC_DS", "QBX_COOP2", "QBX_COOP_MIN_ACC", "QBX_DIGEST_SEG", "QBX_DIGEST_SPREAD",
+        switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_GC_DS", "QBX_COOP2", "QBX_COOP_MIN_ACC", "QBX_ERI_SPILL_THREADS", "QBX_DIGEST_SEG", "QBX_DIGEST_SPREAD",
                                                "QBX_DIGEST_ROWS", "QBX_DEVICE_PAIRS", "QBX_SCHWARZ_SPLIT", "QBX_POOL_GB") if k in os.environ}
         per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
                       "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],

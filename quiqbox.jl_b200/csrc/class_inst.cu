@@ -1,5 +1,7 @@
 // One translation unit per quartet class: compiled 21 times with -DQLA= -DQLB= -DQLC= -DQLD=
 // (build.py), so the classes build in parallel.
+#include <stdlib.h>
+
 #include "digest.cuh"
 
 #define QBX_CAT2(a, b, c, d) qbx_ops_##a##b##c##d
@@ -25,9 +27,20 @@ static int launch_eri(const ClassArgs &a, cudaStream_t s)
                                                                QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES));
         max_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const int64_t need = (a.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    // A/B knob (QBX_ERI_SPILL_THREADS=128 or 64, default off): kernels that spill to local memory run with smaller
+    // blocks, so that the spill working set of an SM fits its L1 (ncu, profiles/r01: (dp|pp) writes 1.2 GB of spills to DRAM)
+    static int threads = 0;
+    if (threads == 0) {
+        threads = QBX_ERI_THREADS;
+        const char *e = getenv("QBX_ERI_SPILL_THREADS");
+        cudaFuncAttributes fa;
+        if (e && atoi(e) >= 32 && atoi(e) <= QBX_ERI_THREADS && atoi(e) % 32 == 0 &&
+            cudaFuncGetAttributes(&fa, eri_class_kernel<QLA, QLB, QLC, QLD>) == cudaSuccess && fa.localSizeBytes > 256)
+            threads = atoi(e);
+    }
+    const int64_t need = (a.ntasks + threads - 1) / threads;
     const unsigned grid = (unsigned)(need < max_blocks ? need : max_blocks);
-    eri_class_kernel<QLA, QLB, QLC, QLD><<<grid, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
+    eri_class_kernel<QLA, QLB, QLC, QLD><<<grid, threads, QBX_BOYS_SMEM_BYTES, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
     }

@@ -248,5 +248,7 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t localSizeBytes, sharedSizeBytes; int numRegs, maxThreadsPerBlock; };
+template <class K> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, K) { memset(a, 0, sizeof(*a)); if (getenv("QBX_EMU_FAKE_SPILL")) a->localSizeBytes = 1024; return cudaSuccess; }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }

@@ -31,6 +31,8 @@ echo "== row-resident digestion (opt-in candidate)"
 QBX_DIGEST_ROWS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10_rows.json" 2> "$OUT/bench_s10_rows.err"
 echo "== spilling thread kernels (dp|pp), (dp|ds), (dd|ps) through the cooperative kernel instead"
 QBX_COOP_MIN_ACC=90 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10_coopmin90.json" 2> "$OUT/bench_s10_coopmin90.err"
+echo "== spilling ERI thread kernels with 128-thread blocks"
+QBX_ERI_SPILL_THREADS=128 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10_spill128.json" 2> "$OUT/bench_s10_spill128.err"
 echo "== (ds|ss) through the general-contraction kernel as well"
 QBX_GC_DS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_s10_gcds.json" 2> "$OUT/bench_s10_gcds.err"
 echo "== cooperative kernel A/B: first-generation interpreter"
