@@ -41,7 +41,7 @@ print("RESULT", i["n_values"], i["n_quartets"], dt)
 
 
 def run(waters=4, procs=None):
-    procs = procs or os.cpu_count() or 1
+    procs = procs or min(os.cpu_count() or 1, 32)          # one single-threaded process per core, at most 32
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
     import emu
     emu.build()                                                   # once, before the workers race for it
