@@ -93,3 +93,49 @@ def test_empty_quartet_list_and_zero_densities(backend):
     Z = np.zeros((db.nbf, db.nbf))
     G = qb.DeviceERI(db, screen_tol=0.0).getGcore(Z, [Z, Z])
     assert len(G) == 2 and not np.any(G[0]) and not np.any(G[1])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_bases(backend, seed):
+    """Random shells (l <= 2, 1-4 primitives, 2-3 centres, some coincident; exponents 1e-2..1e4 for s, ..1e2 for p,
+    ..1e1 for d, the ranges of first- and second-row basis sets): full tensor and Fock build against the oracle."""
+    rng = np.random.RandomState(1000 + seed)
+    centres = [tuple(rng.uniform(-2.5, 2.5, 3)) for _ in range(3)]
+    bs = []
+    for _ in range(rng.randint(2, 6)):
+        l = int(rng.randint(0, 3))
+        k = int(rng.randint(1, 5))
+        xp = list(10 ** rng.uniform(-2, (4, 2, 1)[l], k))
+        co = list(rng.uniform(-1, 1, k))
+        bs += shell(centres[rng.randint(0, 3)], xp, co, l)
+    db = qb.DeviceBasis(bs)
+    ob = oracle.OracleBasis(db.data)
+    n = db.nbf
+    Tref = ob.eri_tensor(canonical=True)
+    scale = max(1.0, float(np.max(np.abs(Tref))))
+    assert np.max(np.abs(qb.elecRepulsions(db) - Tref)) < 1e-10 * scale
+    DJ, DK = rand_sym(n, 7), rand_sym(n, 8)
+    Gref = oracle.getGcore(Tref, DJ, DK)
+    for mode, tol in (("stored", 0.0), ("direct", 0.0), ("stored", 1e-14)):
+        G = qb.DeviceERI(db, mode=mode, screen_tol=tol).getGcore(DJ, [DK])[0]
+        assert np.max(np.abs(G - Gref)) < 1e-9 * max(1.0, float(np.max(np.abs(Gref)))), (mode, tol)
+
+
+def test_tight_contracted_d_shells_conditioning_limit(backend):
+    """KNOWN LIMIT (DESIGN.md decision 7): the shell-level electron transfer [e0|f0] -> [e0|f+1,0] multiplies by
+    zeta/eta per level, so a CONTRACTED d shell with a tight primitive (exponent 285 here, as in transition-metal
+    sets; first-row d shells are single primitives of exponent ~1) loses digits in (dd|dd): 2e-7 of the largest
+    tensor element in this case (1e-9 with a tight exponent of 30, 4e-12 with 3), where the per-function kernel -- the reference's own route -- is exact to 1e-16.
+    The test pins the size of the effect so that it cannot silently grow; the fix (vertical recurrence on both
+    electrons, or a per-primitive choice of the transfer direction) is on the gap list."""
+    c1, c2 = (-0.31, 1.92, 0.44), (1.27, -0.65, 2.03)
+    bs = shell(c1, [284.982, 2.254, 0.124], [0.55, -0.71, 0.32], 2) + shell(c2, [0.293], [1.0], 2)
+    db = qb.DeviceBasis(bs)
+    ob = oracle.OracleBasis(db.data)
+    Tref = ob.eri_tensor(canonical=True)
+    scale = float(np.max(np.abs(Tref)))
+    T = qb.elecRepulsions(db)                                            # class (cooperative) kernels
+    err = float(np.max(np.abs(T - Tref))) / scale
+    assert err < 2e-6, err                                               # today: 2e-7; the 1e-10 bar is NOT met here
+    idx = np.array(np.unravel_index(np.argmax(np.abs(T - Tref)), T.shape))[None, :]
+    assert abs(qb.elecRepulsionList(db, idx)[0] - Tref[tuple(idx[0])]) < 1e-10 * scale     # per-function kernel: fine
