@@ -284,12 +284,12 @@ __device__ __forceinline__ Op ld_op(const Op *ops, int i, int n)
 // Vertical recurrence of one primitive quartet, table-driven (shared by both cooperative kernels):
 // B[0..L] holds the scaled Boys values on entry, the V region [e0|00]^(m) on exit.
 __device__ __forceinline__ void coop_vrr(const CoopArgs &p, double *B, int lane, const double (&PA)[3], const double (&WP)[3],
-                                         double i2z, double rz)
+                                         double i2z, double rz, int nlev = 99)
 {
     // Entries of one level are independent, so each lane takes COOP_BATCH of them at a
     // time: all op records first (global, L1/L2), then all sources (shared), then the
     // arithmetic and the stores -- otherwise every entry pays the full load latency.
-    for (int lv = 0; lv < p.nvrr; ++lv) {
+    for (int lv = 0; lv < p.nvrr && lv < nlev; ++lv) {
         const Op *ops = p.ops + p.vrr[lv].first;
         const int n = p.vrr[lv].count;
         for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
@@ -438,22 +438,24 @@ struct Coop2 {
     static constexpr int E = LA + LB, F = LC + LD, L = E + F;
     static constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NAB = NA * NB;
     static constexpr int NACC = NCSUM(LA, E), NKET = NCSUM(LC, F);
-    static constexpr int GT = S1(L + 1);                       // all stacked bra components, degrees 0..L
+    static constexpr int GT = S1(E + 1);                       // stacked bra components that take part: degrees 0..E
     static constexpr int GB = S1(LA);                          // lane 0 of pass 0 owns the first contracted component
     static_assert(F >= 1 && NACC <= 32 && NKET <= 32, "Coop2: class outside the layout's assumptions");
-    // transfer level f keeps degrees e in [elo(f), ehi(f)] = global stacked range [glo(f), ghi(f))
+    // ket level f keeps degrees e in [elo(f), E] = global stacked range [glo(f), ghi(f)), at orders m = 0..F-f
     static __host__ __device__ constexpr int elo(int f) { return (LA - (F - f)) > 0 ? (LA - (F - f)) : 0; }
-    static __host__ __device__ constexpr int ehi(int f) { return E + (F - f); }
+    static __host__ __device__ constexpr int ehi(int) { return E; }
+    static __host__ __device__ constexpr int nm(int f) { return F - f + 1; }
     static __host__ __device__ constexpr int glo(int f) { return S1(elo(f)); }
     static __host__ __device__ constexpr int ghi(int f) { return S1(ehi(f) + 1); }
     static __host__ __device__ constexpr int rl(int f) { return ghi(f) - glo(f); }
     static constexpr int VT = VLay<L>::total;                  // V region: [e0|00]^(m), layout of VLay<L>
-    static __host__ __device__ constexpr int woff(int f)       // level f: [cf][g - glo(f)], level 0 = V at m = 0, stacked
+    static __host__ __device__ constexpr int woff(int f)       // level f: [m][cf][g - glo(f)]; level 0 = V, orders 0..F, stacked
     {
         int o = VT;
-        for (int x = 0; x < f; ++x) o += NC(x) * rl(x);
+        for (int x = 0; x < f; ++x) o += nm(x) * NC(x) * rl(x);
         return o;
     }
+    static __host__ __device__ constexpr int row(int f, int m, int cf) { return woff(f) + (m * NC(f) + cf) * rl(f) - glo(f); }
     static constexpr int WT = woff(F + 1);
     // after the primitive loops the W levels are dead: ACC2[kk][ASTR] and X2[ab][XSTR] (odd strides) go there
     static constexpr int ASTR = NACC | 1, XSTR = NKET | 1;
@@ -469,9 +471,10 @@ struct Coop2 {
 
     struct LaneInfo {            // per pass
         int g;                   // own stacked index (or -1: lane idle in this pass)
-        const double *v0;        // [g|0]^(0) in the V region
-        double *gp;              // B + g, B + (g + 1_ax), B + (g - 1_ax): a level's row start (a constant) is added
-        const double *up[3], *dn[3];   //   at the point of use, so every access is one LDS/STS with an immediate offset
+        const double *v0;        // [g|0]^(0) in the V region, order m at v0[m * vs]
+        int vs;                  // NC(degree of g)
+        double *gp;              // B + g and B + (g - 1_ax): a level's row start (a constant) is added at the point of
+        const double *dn[3];     //   use, so every access is one LDS/STS with an immediate offset
         double n[3];             // (i, j, k) of g
     };
 
@@ -486,19 +489,24 @@ struct Coop2 {
         while ((r + 1) * (r + 2) / 2 <= c) ++r;
         const int k = c - r * (r + 1) / 2, j = r - k, i = e - r;
         I.v0 = B + VLay<L>::off(e) + c;
+        I.vs = NC(e);
         I.gp = B + g;
-        I.up[0] = B + S1(e + 1) + CIDX(j, k); I.up[1] = B + S1(e + 1) + CIDX(j + 1, k); I.up[2] = B + S1(e + 1) + CIDX(j, k + 1);
         I.dn[0] = B + (i > 0 ? S1(e - 1) + CIDX(j, k) : g);
         I.dn[1] = B + (j > 0 ? S1(e - 1) + CIDX(j - 1, k) : g);
         I.dn[2] = B + (k > 0 ? S1(e - 1) + CIDX(j, k - 1) : g);
         I.n[0] = i; I.n[1] = j; I.n[2] = k;
-        if (I.g < 0) { I.v0 = B; I.gp = B; for (int x = 0; x < 3; ++x) { I.up[x] = I.dn[x] = B; I.n[x] = 0.0; } }
+        if (I.g < 0) { I.v0 = B; I.vs = 0; I.gp = B; for (int x = 0; x < 3; ++x) { I.dn[x] = B; I.n[x] = 0.0; } }
     }
 
-    // build level FL + 1 from FL (and FL - 1), then recurse
+    // Vertical recurrence on the KET (Obara-Saika, centre C), level FL -> FL + 1 at orders m = 0..F-FL-1:
+    //   [g|cf]^(m) = QC_ax [g|cf1]^(m) + WQ_ax [g|cf1]^(m+1) + nf/(2 eta) ([g|cf2]^(m) - (rho/eta) [g|cf2]^(m+1))
+    //                + n_ax(g) / (2 (zeta + eta)) [g - 1_ax|cf1]^(m+1)
+    // ax, cf1, cf2, nf depend on the ket component only (constants after unrolling); everything except the last
+    // term is the lane's own column.  Unlike the electron transfer of the thread kernels and of the interpreter
+    // (decision 7) nothing here is multiplied by zeta/eta, so contracted tight d shells keep their digits.
     template <int FL>
-    static __device__ __forceinline__ void transfer(const LaneInfo (&I)[NP], const double (&nae)[NP][3],
-                                                    const double (&k0)[3], double zoe, double i2e, double (&acc)[NKET], int lane)
+    static __device__ __forceinline__ void ket_vrr(const LaneInfo (&I)[NP], const double (&nh)[NP][3], const double (&QC)[3],
+                                                   const double (&WQ)[3], double i2e, double rhoe, double (&acc)[NKET], int lane)
     {
         if constexpr (FL < F) {
             constexpr int f1 = FL + 1;
@@ -512,25 +520,26 @@ struct Coop2 {
                     const int nf = (ax == 0 ? fi : (ax == 1 ? fj : kf)) - 1;
                     const int cf = CIDX(fj, kf), cf1 = CIDX(fj1, fk1);
                     const int cf2 = nf > 0 ? CIDX(fj1 - (ax == 1), fk1 - (ax == 2)) : 0;
-                    // row starts relative to B + g (compile-time constants once the loops are unrolled)
-                    const int src = woff(FL) + cf1 * rl(FL) - glo(FL);
-                    const int src2 = woff(FL > 0 ? FL - 1 : 0) + cf2 * rl(FL > 0 ? FL - 1 : 0) - glo(FL > 0 ? FL - 1 : 0);
-                    const int dst = woff(f1) + cf * rl(f1) - glo(f1);
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) {
-                        if (!pass_in_level(q, f1)) continue;
-                        const int g = I[q].g;
-                        if (g >= glo(f1) && g < ghi(f1)) {
-                            double v = fma(k0[ax], I[q].gp[src], -zoe * I[q].up[ax][src]);
-                            v = fma(nae[q][ax], I[q].dn[ax][src], v);
-                            if (nf > 0) v = fma(nf * i2e, I[q].gp[src2], v);
-                            I[q].gp[dst] = v;
-                            if (f1 >= LC && q == 0 && lane < NACC) acc[NCSUM(LC, f1 - 1) + cf] += v;
+                    for (int m = 0; m < nm(f1); ++m) {
+                        const int s0 = row(FL, m, cf1), s1 = row(FL, m + 1, cf1), dst = row(f1, m, cf);
+                        const int t0 = row(FL > 0 ? FL - 1 : 0, m, cf2), t1 = row(FL > 0 ? FL - 1 : 0, m + 1, cf2);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (!pass_in_level(q, f1)) continue;
+                            const int g = I[q].g;
+                            if (g >= glo(f1) && g < ghi(f1)) {
+                                double v = fma(QC[ax], I[q].gp[s0], WQ[ax] * I[q].gp[s1]);
+                                if (nf > 0) v = fma(nf * i2e, fma(-rhoe, I[q].gp[t1], I[q].gp[t0]), v);
+                                v = fma(nh[q][ax], I[q].dn[ax][s1], v);
+                                I[q].gp[dst] = v;
+                                if (m == 0 && f1 >= LC && q == 0 && lane < NACC) acc[NCSUM(LC, f1 - 1) + cf] += v;
+                            }
                         }
                     }
                 }
             __syncwarp();
-            transfer<FL + 1>(I, nae, k0, zoe, i2e, acc, lane);
+            ket_vrr<FL + 1>(I, nh, QC, WQ, i2e, rhoe, acc, lane);
         }
     }
 };
@@ -550,7 +559,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop2_kernel(CoopArgs p)
         const int2 t = p.tasks[qt];
         const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
         const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
-        const double CD[3] = {gk[3], gk[4], gk[5]};
+        const double Cc[3] = {gk[0], gk[1], gk[2]}, CD[3] = {gk[3], gk[4], gk[5]};
         const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
         const int pk0 = p.ket.prim_off[t.y], pk1 = p.ket.prim_off[t.y + 1];
         double acc[C2::NKET];
@@ -569,29 +578,32 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop2_kernel(CoopArgs p)
                 const double PQ[3] = {P[0] - Q[0], P[1] - Q[1], P[2] - Q[2]};
                 const double T = zeta * rz * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
                 const double WP[3] = {-rz * PQ[0], -rz * PQ[1], -rz * PQ[2]};
-                const double ie = 2.0 * i2e, zoe = zeta * ie;
-                const double k0[3] = {-(bx * AB[0] + dx * CD[0]) * ie, -(bx * AB[1] + dx * CD[1]) * ie,
-                                      -(bx * AB[2] + dx * CD[2]) * ie};
+                const double rhoe = 1.0 - rz, hinv = 0.5 * inv;       // rho/eta = zeta/(zeta+eta); 1/(2(zeta+eta))
+                const double QC[3] = {Q[0] - Cc[0], Q[1] - Cc[1], Q[2] - Cc[2]};
+                const double WQ[3] = {rhoe * PQ[0], rhoe * PQ[1], rhoe * PQ[2]};
                 double Fm[9];
                 boys_rt(p.boys, p.boys_inv, T, Kab * Kcd * rs, C2::L, Fm);
                 __syncwarp();                              // the previous primitive's level-0 copy has read V
                 if (lane <= C2::L) B[lane] = Fm[lane];
                 __syncwarp();
-                coop_vrr(p, B, lane, PA, WP, i2z, rz);
-                // level 0 of the transfer = V at m = 0, copied into the stacked layout
-                double nae[C2::NP][3];
+                coop_vrr(p, B, lane, PA, WP, i2z, rz, C2::E);          // bra degrees 0..E only, all orders
+                // level 0 of the ket recurrence = V at orders 0..F, copied into the stacked layout
+                double nh[C2::NP][3];
 #pragma unroll
                 for (int q = 0; q < C2::NP; ++q) {
                     const int g = I[q].g;
-                    if (g >= C2::glo(0)) I[q].gp[C2::woff(0) - C2::glo(0)] = *I[q].v0;
+                    if (g >= C2::glo(0)) {
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) nae[q][x] = I[q].n[x] * i2e;
+                        for (int m = 0; m < C2::nm(0); ++m) I[q].gp[C2::row(0, m, 0)] = I[q].v0[m * I[q].vs];
+                    }
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) nh[q][x] = I[q].n[x] * hinv;
                 }
                 if constexpr (LC == 0) {
                     if (lane < C2::NACC) acc[0] += *I[0].v0;
                 }
                 __syncwarp();
-                C2::template transfer<0>(I, nae, k0, zoe, i2e, acc, lane);
+                C2::template ket_vrr<0>(I, nh, QC, WQ, i2e, rhoe, acc, lane);
             }
         }
         // contracted [e0|f0] -> shared, one row per stacked ket component

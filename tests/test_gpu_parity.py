@@ -443,9 +443,12 @@ def test_allocation_pool_reuse_and_trim():
 
 # ------------------------------------------------------------------ new in the last commits of round 1 (kept last: pytest -x)
 def test_cooperative_kernel_generations_agree():
-    """The compiled cooperative kernel (eri_coop2_kernel: lane = stacked bra component, QBX_COOP2=1, default) and
-    the table-driven interpreter (QBX_COOP2=0) execute the same recurrences in the same order: on synthetic
-    batches of every class the former serves their checksums agree to the rounding of the (atomic, order-dependent) final sum."""
+    """The compiled cooperative kernel (eri_coop2_kernel: lane = stacked bra component, vertical recurrence on the
+    ket, QBX_COOP2=1, default) against the table-driven first generation (QBX_COOP2=0, electron transfer) on
+    synthetic batches of every class the former serves.  They are different recurrences: on these batches
+    (exponents over four decades) the transfer loses up to ~1e-8 of a checksum, see DESIGN.md decisions 7 and 16;
+    each is checked against the oracle in test_synthetic_class_batch_vs_oracle.  This test guards against gross
+    disagreement (a wrong index, a missing term)."""
     import subprocess
     import sys
     code = r'''
@@ -471,4 +474,4 @@ for cls in [(2,1,2,1),(2,2,1,1),(2,2,2,0),(2,2,2,1),(2,2,2,2)]:
         vals.append([float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("CHK")])
     assert len(vals[0]) == 10 and len(vals[1]) == 10
     for a, b in zip(*vals):
-        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (a, b)        # the checksum itself is an atomic sum: order-dependent rounding
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (a, b)
