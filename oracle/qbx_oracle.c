@@ -595,3 +595,86 @@ void orc_getGcore(int64_t N, const double *H, const double *DJ, const double *DK
         G[nu + N * mu] = accJ - accK;
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Packed (sparse) unique-quartet store + getGcore on it.  Same integrals and the same   */
+/* contraction as orc_eri_tensor + orc_getGcore above, without the N^4 array, so that     */
+/* the oracle can run an SCF at sizes whose dense tensor does not fit ((H2O)8: 12.8 GB,   */
+/* (H2O)16: 204.8 GB).  Unique entries are the reference's (Framework.jl:651-653):       */
+/* p = (i <= j), q = (k <= l), q <= p; an entry is skipped when its Cauchy-Schwarz bound  */
+/* sqrt((ij|ij) (kl|kl)) is below `tol` (a rigorous bound on |(ij|kl)|).                  */
+/* ------------------------------------------------------------------------------------ */
+void orc_schwarz(const orc_basis *b, double *Q /* N(N+1)/2 */)
+{
+    int64_t N = b->nbf, M = N * (N + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < M; ++p) {
+        int64_t i, j;
+        orc_tri2(p, &i, &j);
+        Q[p] = sqrt(fabs(orc_eri_quartet_canonical(b, i, j, i, j)));
+    }
+}
+
+/* cnt[p - p0] = surviving q <= p, rows p0 <= p < p1 */
+void orc_packed_count(int64_t p0, int64_t p1, const double *Q, double tol, int64_t *cnt)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = p0; p < p1; ++p) {
+        int64_t c = 0;
+        for (int64_t q = 0; q <= p; ++q) c += (Q[p] * Q[q] >= tol);
+        cnt[p - p0] = c;
+    }
+}
+
+/* rows p0 <= p < p1; off[p - p0] = position of row p's first entry in col/val */
+void orc_packed_fill(const orc_basis *b, int64_t p0, int64_t p1, const double *Q, double tol, const int64_t *off,
+                     int32_t *col, double *val)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t p = p1 - 1; p >= p0; --p) {
+        int64_t i, j, k, l, n = off[p - p0];
+        orc_tri2(p, &i, &j);
+        for (int64_t q = 0; q <= p; ++q) {
+            if (Q[p] * Q[q] < tol) continue;
+            orc_tri2(q, &k, &l);
+            col[n] = (int32_t)q;
+            val[n++] = orc_eri_quartet_canonical(b, i, j, k, l);
+        }
+    }
+}
+
+/* getGcore (HartreeFock.jl:305-319) over the packed store: every distinct permutational image
+ * (a b|c d) of a stored value v adds DJ[d,c] v to G[a,b] and -DK[b,c] v to G[a,d] -- the two sums of
+ * the reference's formula, term by term; no symmetry of DJ / DK is assumed.  G is accumulated (+=):
+ * the caller zeroes it and may call this once per block of rows. */
+void orc_packed_gcore(int64_t N, int64_t p0, int64_t p1, const int64_t *off, const int32_t *col, const double *val,
+                      const double *DJ, const double *DK, double *G)
+{
+#pragma omp parallel
+    {
+        double *g = (double *)calloc((size_t)(N * N), sizeof(double));
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t p = p0; p < p1; ++p) {
+            int64_t i, j, k, l;
+            orc_tri2(p, &i, &j);
+            for (int64_t n = off[p - p0]; n < off[p - p0 + 1]; ++n) {
+                const int64_t q = col[n];
+                const double v = val[n];
+                orc_tri2(q, &k, &l);
+                for (int img = 0; img < 8; ++img) {
+                    if ((img & 1) && i == j) continue;
+                    if ((img & 2) && k == l) continue;
+                    if ((img & 4) && p == q) continue;
+                    int64_t a = (img & 1) ? j : i, bb = (img & 1) ? i : j;
+                    int64_t c = (img & 2) ? l : k, d = (img & 2) ? k : l;
+                    if (img & 4) { int64_t t = a; a = c; c = t; t = bb; bb = d; d = t; }
+                    g[a + N * bb] += DJ[d + N * c] * v;
+                    g[a + N * d] -= DK[bb + N * c] * v;
+                }
+            }
+        }
+#pragma omp critical
+        for (int64_t x = 0; x < N * N; ++x) G[x] += g[x];
+        free(g);
+    }
+}

@@ -2,6 +2,8 @@
 // (build.py), so the classes build in parallel.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "digest.cuh"
 
 #define QBX_CAT2(a, b, c, d) qbx_ops_##a##b##c##d
@@ -74,31 +76,48 @@ static int launch_digest(const DigestArgs &a, cudaStream_t s)
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }
-// row-resident digestion; -1 = does not apply here (UHF build, rows too long for shared memory): use launch_digest
-static int launch_digest_rows(const DigestArgs &a0, cudaStream_t s)
+// span digestion (digest.cuh); -1 = the K rows of a warp do not fit shared memory: use launch_digest
+static int launch_digest_span(const DigestArgs &a0, cudaStream_t s)
 {
     if (a0.ntasks <= 0) return QBX_OK;
-    const size_t smem = (size_t)digest_rows_doubles<QLA, QLB>(a0.nbf) * sizeof(double);
-    if (a0.nmat != 1 || smem > QBX_ROWS_MAX_SMEM) return -1;
-    static int sms = 0;
-    static size_t attr = 0;
-    if (sms == 0) {
-        int dev = 0;
-        QBX_CUDA(cudaGetDevice(&dev));
-        QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (smem > attr) {
-        QBX_CUDA(cudaFuncSetAttribute(digest_rows_kernel<QLA, QLB, QLC, QLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+    constexpr int NCOMP = EriClass<QLA, QLB, QLC, QLD>::NCOMP;
+    const size_t per_warp = (size_t)digest_span_doubles<QLA, QLB>(a0.wC + a0.wD, a0.nmat) * sizeof(double);
+    // warps per block: 8 when two or more such blocks fit an SM, else as many warps as fit (one block per SM)
+    int wpb = QBX_SPAN_MAX_WARPS;
+    if (2 * wpb * per_warp > QBX_SPAN_MAX_SMEM) wpb = (int)(QBX_SPAN_MAX_SMEM / per_warp) < wpb ? (int)(QBX_SPAN_MAX_SMEM / per_warp) : wpb;
+    if (wpb < 1) return -1;
+    const size_t smem = wpb * per_warp;
+    static std::mutex mu;
+    static int sms = 0, per_sm[QBX_SPAN_MAX_WARPS + 1] = {0};
+    static size_t attr = 0, occ_smem[QBX_SPAN_MAX_WARPS + 1] = {0};
+    int blocks_per_sm;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (sms == 0) {
+            int dev = 0;
+            QBX_CUDA(cudaGetDevice(&dev));
+            QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        if (smem > attr) {
+            QBX_CUDA(cudaFuncSetAttribute(digest_span_kernel<QLA, QLB, QLC, QLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        if (occ_smem[wpb] != smem) {
+            QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[wpb], digest_span_kernel<QLA, QLB, QLC, QLD>, wpb * 32, smem));
+            if (per_sm[wpb] < 1) per_sm[wpb] = 1;
+            occ_smem[wpb] = smem;
+        }
+        blocks_per_sm = per_sm[wpb];
     }
     DigestArgs a = a0;
-    // span: long enough to amortise loading and flushing the rows, short enough to keep every SM busy
-    int64_t span = a.ntasks / ((int64_t)sms * 8);
-    span = span > 2048 ? 2048 : (span < 128 ? 128 : span / 128 * 128);
+    // span: long enough to amortise flushing the rows, short enough that every resident warp gets several
+    const int64_t warps = (int64_t)sms * blocks_per_sm * wpb;
+    const int64_t span_min = NCOMP >= 100 ? 32 : (NCOMP >= 27 ? 64 : 256);
+    int64_t span = a.ntasks / (warps * 4);
+    span = span > 4096 ? 4096 : (span < span_min ? span_min : span / 32 * 32);
     a.span = (int)span;
-    const int64_t nblk = (a.ntasks + span - 1) / span;
-    const int64_t R = nblk < a.spread ? nblk : a.spread, C = (nblk + R - 1) / R;
-    digest_rows_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(R * C), 128, smem, s>>>(a);
+    const int64_t nspan = (a.ntasks + span - 1) / span, need = (nspan + wpb - 1) / wpb, cap = (int64_t)sms * blocks_per_sm;
+    digest_span_kernel<QLA, QLB, QLC, QLD><<<(unsigned)(need < cap ? need : cap), wpb * 32, smem, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }
@@ -113,6 +132,6 @@ static int launch_scatter(const ScatterArgs &a, cudaStream_t s)
 extern const ClassOps QBX_CAT(QLA, QLB, QLC, QLD);
 const ClassOps QBX_CAT(QLA, QLB, QLC, QLD) = {QLA, QLB, QLC, QLD,
                                               EriClass<QLA, QLB, QLC, QLD>::NCOMP,
-                                              launch_eri, launch_digest, launch_scatter, launch_digest_rows,
+                                              launch_eri, launch_digest, launch_scatter, launch_digest_span,
                                               (QLA == QLC && QLB == QLD && NCSUM(QLA, QLA + QLB) * NCSUM(QLC, QLC + QLD) < QBX_COOP_ACC)
                                                   ? launch_eri_split : nullptr};

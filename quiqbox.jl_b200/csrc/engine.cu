@@ -648,11 +648,42 @@ int Engine::upload(bool pair_adjacent)
             sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({a, b});
         }
     } else {
-        for (size_t a = 0; a < ns; ++a)           // shells are sorted by l, so a >= b implies la >= lb
-            for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
+        // Shell pairs of a class are listed DIAGONAL BY DIAGONAL: (A_(j+k), B_j), j = 0, 1, .. for k = 0, 1, ..  Any 32
+        // consecutive pairs -- and any 32 consecutive survivors of the Schwarz screening -- then consist of 32
+        // different first shells and 32 different second shells, which is what lets the digestion warps update
+        // their shared-memory K rows without atomics or shuffle reductions (digest.cuh).  Shells are sorted by
+        // l, so with A taken from the higher l (or, for equal l, the later shell) a >= b holds as before.
+        std::vector<int> of_l[QBX_MAX_L + 1];
+        for (size_t a = 0; a < ns; ++a) of_l[shells_[a].l].push_back((int)a);
+        for (int la = 0; la <= QBX_MAX_L; ++la)
+            for (int lb = 0; lb <= la; ++lb) {
+                const std::vector<int> &SA = of_l[la], &SB = of_l[lb];
+                auto &out = sp[pair_cls(la, lb)];
+                if (SA.empty() || SB.empty()) continue;
+                if (la == lb) {
+                    const size_t n = SA.size();
+                    for (size_t k = 0; k < n; ++k)
+                        for (size_t j = 0; j + k < n; ++j) out.push_back({SA[j + k], SA[j]});
+                } else {
+                    const size_t nA = SA.size(), nB = SB.size(), M = std::max(nA, nB);
+                    for (size_t k = 0; k < M; ++k) {
+                        if (nA <= nB) for (size_t i = 0; i < nA; ++i) out.push_back({SA[i], SB[(i + k) % M]});
+                        else for (size_t i = 0; i < nB; ++i) out.push_back({SA[(i + k) % M], SB[i]});
+                    }
+                }
+            }
     }
     std::vector<int> first_h(ns);
     { int acc = 0; for (size_t s = 0; s < ns; ++s) { first_h[s] = acc; acc += qbx_nc(shells_[s].l); } }
+    for (int l = 0; l <= QBX_MAX_L; ++l) { l_lo_[l] = 0; l_hi_[l] = 0; }
+    {   // internal function range of every angular momentum (contiguous: shells are sorted by l)
+        bool seen[QBX_MAX_L + 1] = {false};
+        for (size_t s = 0; s < ns; ++s) {
+            const int l = shells_[s].l, lo = first_h[s], hi = first_h[s] + qbx_nc(l);
+            if (!seen[l]) { l_lo_[l] = lo; l_hi_[l] = hi; seen[l] = true; }
+            else { l_lo_[l] = std::min(l_lo_[l], lo); l_hi_[l] = std::max(l_hi_[l], hi); }
+        }
+    }
     // QBX_DEVICE_PAIRS=1: primitive-pair records computed on the device (opt-in, unmeasured)
     static const int dev_pairs = getenv("QBX_DEVICE_PAIRS") ? atoi(getenv("QBX_DEVICE_PAIRS")) : 0;
     DevShells S{nullptr, nullptr, nullptr, nullptr};
@@ -1121,16 +1152,18 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             a.bra_info = pairs_[bc].info; a.ket_info = pairs_[kc].info;
             static const int spread = getenv("QBX_DIGEST_SPREAD") ? atoi(getenv("QBX_DIGEST_SPREAD")) : QBX_DIGEST_SPREAD;
             a.spread = spread > 0 ? spread : 1;
-            static const int seg = getenv("QBX_DIGEST_SEG") ? atoi(getenv("QBX_DIGEST_SEG")) : 1;
-            a.seg = seg;
-            a.span = 128;
-            static const int rows = getenv("QBX_DIGEST_ROWS") ? atoi(getenv("QBX_DIGEST_ROWS")) : 0;     // opt-in, unmeasured
+            a.span = 0;
+            // QBX_DIGEST_SPAN=0: the round-1 kernel (every update a global RED), kept as the fallback for bases whose
+            // K rows do not fit shared memory and for A/B measurements
+            static const int rows = getenv("QBX_DIGEST_SPAN") ? atoi(getenv("QBX_DIGEST_SPAN")) : 1;
             a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
+            a.c0 = l_lo_[ops->lc]; a.wC = l_hi_[ops->lc] - l_lo_[ops->lc];
+            a.d0 = l_lo_[ops->ld]; a.wD = ops->lc == ops->ld ? 0 : l_hi_[ops->ld] - l_lo_[ops->ld];
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
                 cudaStream_t ds = side_[kside++ % kSide];
-                int rc = rows ? ops->digest_rows(a, ds) : -1;
+                int rc = rows ? ops->digest_span(a, ds) : -1;
                 if (rc < 0) rc = ops->digest(a, ds);
                 if (rc) return rc;
                 stats[0] += 1;
@@ -1142,7 +1175,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
                     int rc = run_eri(bc, kc, tl.tasks + o, n, chunk_, s);
                     if (rc) return rc;
                     a.tasks = tl.tasks + o; a.ntasks = n; a.vals = chunk_;
-                    rc = rows ? ops->digest_rows(a, s) : -1;
+                    rc = rows ? ops->digest_span(a, s) : -1;
                     if (rc < 0) rc = ops->digest(a, s);
                     if (rc) return rc;
                     stats[0] += 2;

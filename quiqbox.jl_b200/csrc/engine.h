@@ -26,8 +26,9 @@ struct DigestArgs {
     const double *vals;          // [ncomp][ntasks]
     int nbf, nmat, same_class;   // nbf = internal dimension here
     int spread;                  // number of block slots the task list is dealt over (see digest.cuh)
-    int span;                    // digest_rows_kernel: tasks per block (a multiple of 128)
-    int seg;                     // 1: segmented warp reductions (default); 0: per-lane REDs when a warp is not uniform (QBX_DIGEST_SEG, A/B switch)
+    int span;                    // digest_span_kernel: tasks per warp span (a multiple of 32; set by the launcher)
+    int c0, wC, d0, wD;          // digest_span_kernel: internal functions of the shells C are [c0, c0 + wC), of the shells D
+                                 // [d0, d0 + wD); wD = 0 when both are the same range (lc == ld)
     const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
 };
@@ -46,7 +47,7 @@ struct ClassOps {
     int (*eri)(const ClassArgs &, cudaStream_t);
     int (*digest)(const DigestArgs &, cudaStream_t);
     int (*scatter)(const ScatterArgs &, cudaStream_t);
-    int (*digest_rows)(const DigestArgs &, cudaStream_t);  // row-resident digestion (QBX_DIGEST_ROWS=1); returns -1 when it does not apply
+    int (*digest_span)(const DigestArgs &, cudaStream_t);  // span digestion (K rows in shared memory); returns -1 when the rows do not fit
     int (*eri_split)(const ClassArgs &, cudaStream_t);     // one warp per task (diagonal classes only, else null)
 };
 const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
@@ -160,6 +161,7 @@ private:
     double *d_Jt_ = nullptr, *d_Kt_ = nullptr;
     int *d_shell_first_ = nullptr, *d_ext_of_int_ = nullptr;
     int64_t nint_ = 0;                   // internal dimension (complete Cartesian shells)
+    int l_lo_[QBX_MAX_L + 1] = {0}, l_hi_[QBX_MAX_L + 1] = {0};   // internal functions of angular momentum l: [l_lo, l_hi)
     double *d_Dint_ = nullptr;           // DJ, DK[0], DK[1] in internal numbering
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;

@@ -139,3 +139,100 @@ def getGcore_general(H, DJ, DK):
     """Same contraction as getGcore for a tensor WITHOUT permutational symmetry (used by the
     multi-rank CPU test, where each rank holds a slice): every (mu, nu) computed, no mirroring."""
     return np.einsum("sl,mnls->mn", DJ, H) - np.einsum("ls,mlsn->mn", DK, H)
+
+
+class PackedERI:
+    """Schwarz-screened unique quartets of the oracle in CSR form (orc_packed_*): the oracle's own
+    integrals and getGcore formula without the N^4 array, for SCF runs at (H2O)8 / (H2O)16 size.
+    `block` rows are computed per C call so that progress can be reported and checkpointed."""
+
+    def __init__(self, ob, tol=1e-13, block=512, log=None, checkpoint=None):
+        self.ob, self.n = ob, ob.nbf
+        n = self.n
+        M = n * (n + 1) // 2
+        L = lib()
+        Q = np.zeros(M)
+        L.orc_schwarz(C.byref(ob.s), _p(Q))
+        cnt = np.zeros(M, dtype=np.int64)
+        L.orc_packed_count(C.c_int64(0), C.c_int64(M), _p(Q), C.c_double(tol), _p(cnt))
+        self.off = np.zeros(M + 1, dtype=np.int64)
+        np.cumsum(cnt, out=self.off[1:])
+        nnz = int(self.off[-1])
+        self.nnz, self.M, self.tol = nnz, M, tol
+        if log:
+            log(f"packed oracle store: N = {n}, {nnz:.4e} of {M * (M + 1) // 2:.4e} unique entries survive tol = {tol:g}")
+        if checkpoint and os.path.exists(checkpoint + ".val.npy"):
+            self.col = np.load(checkpoint + ".col.npy", mmap_mode="r+")
+            self.val = np.load(checkpoint + ".val.npy", mmap_mode="r+")
+            done = int(np.load(checkpoint + ".done.npy"))
+            assert len(self.val) == nnz
+        else:
+            if checkpoint:
+                self.col = np.lib.format.open_memmap(checkpoint + ".col.npy", mode="w+", dtype=np.int32, shape=(nnz,))
+                self.val = np.lib.format.open_memmap(checkpoint + ".val.npy", mode="w+", dtype=np.float64, shape=(nnz,))
+            else:
+                self.col = np.zeros(nnz, dtype=np.int32)
+                self.val = np.zeros(nnz)
+            done = M
+        import time
+        t0 = time.time()
+        p1 = done
+        while p1 > 0:                                  # long rows first
+            p0 = max(0, p1 - block)
+            o = np.ascontiguousarray(self.off[p0:p1 + 1])
+            L.orc_packed_fill(C.byref(ob.s), C.c_int64(p0), C.c_int64(p1), _p(Q), C.c_double(tol), _p(o),
+                              C.c_void_p(self.col.ctypes.data), C.c_void_p(self.val.ctypes.data))
+            p1 = p0
+            if checkpoint:
+                np.save(checkpoint + ".done.npy", np.int64(p1))
+            if log:
+                frac = 1.0 - self.off[p1] / max(nnz, 1)
+                log(f"  rows >= {p1}: {100 * frac:.1f} % of the entries, {time.time() - t0:.0f} s")
+        self.col = np.asarray(self.col)
+        self.val = np.asarray(self.val)
+
+    def getGcore(self, DJ, DK):
+        n = self.n
+        G = np.zeros((n, n), order="F")
+        lib().orc_packed_gcore(C.c_int64(n), C.c_int64(0), C.c_int64(self.M), _p(self.off), C.c_void_p(self.col.ctypes.data),
+                               C.c_void_p(self.val.ctypes.data), _p(np.asfortranarray(DJ, dtype=np.float64)),
+                               _p(np.asfortranarray(DK, dtype=np.float64)), C.c_void_p(G.ctypes.data))
+        return np.ascontiguousarray(G)
+
+    def gcore(self):
+        return lambda DJ, DKs: [self.getGcore(DJ, DK) for DK in DKs]
+
+
+# ---- quad-precision arbiter (oracle/qbx_oracle_q.c) -------------------------------------------------
+def prim_eri_quad(p1, p2, p3, p4):
+    """The reference's primitive routine evaluated in __float128, rounded once to double."""
+    cen, xpn, ang = _prim_args([p1, p2, p3, p4])
+    L = lib()
+    L.orcq_prim_eri_d.restype = C.c_double
+    L.orcq_prim_eri_d.argtypes = [C.c_void_p] * 3
+    return L.orcq_prim_eri_d(_p(cen), _p(xpn), _p(ang))
+
+
+def prim_eri_shared_text_double(p1, p2, p3, p4):
+    """Double instantiation of the text the arbiter shares with the oracle (must equal prim_eri bit for bit)."""
+    cen, xpn, ang = _prim_args([p1, p2, p3, p4])
+    L = lib()
+    L.orcd_prim_eri_d.restype = C.c_double
+    L.orcd_prim_eri_d.argtypes = [C.c_void_p] * 3
+    return L.orcd_prim_eri_d(_p(cen), _p(xpn), _p(ang))
+
+
+def boys_quad(x, n):
+    L = lib()
+    L.orcq_boys_d.restype = C.c_double
+    L.orcq_boys_d.argtypes = [C.c_double, C.c_int]
+    return L.orcq_boys_d(float(x), int(n))
+
+
+def eri_list_quad(ob, ijkl):
+    """Contracted integrals of an OracleBasis through the quad-precision arbiter (any index order: in quad
+    precision the orientation does not matter)."""
+    ijkl = np.ascontiguousarray(ijkl, dtype=np.int64).reshape(-1, 4)
+    out = np.zeros(len(ijkl))
+    lib().orcq_eri_list(C.byref(ob.s), C.c_int64(len(ijkl)), _p(ijkl), _p(out))
+    return out

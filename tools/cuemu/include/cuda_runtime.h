@@ -183,6 +183,21 @@ static inline int __all_sync(unsigned m, int pred)
     return b == cuemu::active_mask(p);
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+// lanes (among the live ones) that hold the same value as the caller
+template <class T> static inline unsigned __match_any_sync(unsigned, T v)
+{
+    static_assert(sizeof(T) <= 8, "match of a type wider than 64 bits");
+    const int p = cuemu::xchg_parity();
+    uint64_t w = 0;
+    memcpy(&w, &v, sizeof(T));
+    *cuemu::xchg_slot(p, cuemu::cur->lane) = w;
+    cuemu::warp_barrier();
+    const unsigned act = cuemu::active_mask(p);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (((act >> l) & 1u) && *cuemu::xchg_slot(p, l) == w) r |= 1u << l;
+    return r;
+}
 
 // ------------------------------------------------------------------ host API
 typedef int cudaError_t;
