@@ -8,8 +8,8 @@ list is sharded over the ranks (strong scaling: the molecule is fixed).
 One *step* = one pass of the hot path over the whole shard:
     (1) every unique contracted ERI of the shard recomputed by the shell-class kernels into
         the packed store (qbx_eri_recompute_async), then
-    (2) one RHF Fock build: J/K digestion of the packed store (qbx_fock_build_device) and,
-        for N > 1, the NCCL all-reduce of the partial G matrices.
+    (2) one RHF Fock build: J/K digestion of the packed store (qbx_fock_build_device), which for
+        N > 1 ends in the library's own NCCL all-reduce of the partial G matrices (qbx_comm_init).
 `value` = unique contracted ERIs of the whole job / step time (contracted ERIs/s); the Fock
 build alone (stored mode, the per-SCF-iteration cost) is reported as `fock_build_ms`.
 Inputs are resident in HBM; the packed store (10.7 GB at N = 1 with the default 1e-12 Schwarz
@@ -114,6 +114,28 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores():
+    """Cores this process may run on (the box's, not what a launcher put into OMP_NUM_THREADS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_threads():
+    """Set the oracle's OpenMP team to all host cores and return the team size that really runs.
+    torch.distributed.run exports OMP_NUM_THREADS=1: without this the N >= 2 reference arm of round 1 ran on one
+    thread while reporting every core."""
+    import oracle
+    return int(oracle.lib().orc_set_threads(host_cores()))
+
+
+def bench_config(label, n, screen):
+    """The workload description: identical in the GPU arm and in the reference arm."""
+    return {"workload": label, "basis": "cc-pVDZ", "scf": "RHF", "nbf": n, "unique_eris_unscreened": unique_count(n),
+            "screen_tol": screen}
+
+
 def cpu_sample(bs, seconds, parallel=True):
     """Time the CPU oracle on uniformly sampled unique function quartets of the workload."""
     import oracle
@@ -132,14 +154,38 @@ def cpu_sample(bs, seconds, parallel=True):
     return done / t_used, done, t_used
 
 
+def cpu_fock_sample(n_small=120, n_target=400, reps=3):
+    """The second half of the metric on the CPU: the reference's getGcore (HartreeFock.jl:305-319, restated in
+    orc_getGcore: 2 N^4 multiply-adds over the DENSE tensor, threads over the (mu, nu) pairs) timed on a dense
+    N = 120 tensor -- benzene/cc-pVDZ size, 1.66 GB; the cost does not depend on the values, so the tensor is
+    synthetic -- and scaled by (N_target / 120)^4 to the workload (whose dense tensor, 204.8 GB, the reference
+    could not even allocate).  Returns (seconds at n_small, extrapolated seconds at n_target)."""
+    import oracle
+    rng = np.random.RandomState(7)
+    H = np.empty(n_small ** 4)
+    blk = rng.uniform(-1, 1, n_small ** 2)
+    for i in range(n_small ** 2):                                      # cheap fill; values are irrelevant to the timing
+        H[i * n_small ** 2:(i + 1) * n_small ** 2] = blk
+    H = H.reshape((n_small,) * 4, order="F")
+    D = rng.uniform(-1, 1, (n_small, n_small)); D = (D + D.T) / 2
+    oracle.getGcore(H, 2 * D, D)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.getGcore(H, 2 * D, D)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return t, t * (n_target / n_small) ** 4
+
+
 def run_reference(args):
     """Reference arm: the CPU restatement of the reference's algorithm (the reference is pure
-    Julia and cannot be installed here: no julia binary, no network -- see DESIGN.md)."""
+    Julia and cannot be installed here: no julia binary, no network -- see DESIGN.md), on ALL host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     label, nuc, xyz, bs = workload(args.workload)
-    cores = os.cpu_count()
+    threads = cpu_threads()
     per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_sample(bs, per_step)
@@ -148,13 +194,18 @@ def run_reference(args):
         r, n, t = cpu_sample(bs, per_step)
         rates.append(r); tot_t += t; tot_n += n
     v = tot_n / tot_t
+    f_small, f_target = cpu_fock_sample(n_target=len(bs))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label, "nbf": len(bs), "unique_eris": unique_count(len(bs))},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{tot_n} uniformly sampled contracted ERIs of {label} per run, OpenMP over quartets, "
-                                       "per-primitive-component Obara-Saika as in the reference"},
+            "config": bench_config(label, len(bs), args.screen),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{tot_n} uniformly sampled contracted ERIs of {label} per run, OpenMP over quartets "
+                                       f"({threads} threads, set explicitly), per-primitive-component Obara-Saika as in the reference",
+                             "fock_build_s": f_target, "fock_build_s_measured_n120": f_small,
+                             "fock_build_rule": "orc_getGcore (= HartreeFock.jl:305-319) on a dense N = 120 tensor, x (N/120)^4"},
+            "secondary_metric": {"metric": "rhf_fock_build_seconds_per_iter", "value": f_target, "unit": "s", "higher_is_better": False,
+                                 "note": "extrapolated from N = 120, see cpu_baseline.fock_build_rule"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -190,6 +241,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.init(local)
     lib = L.load()
+    if world > 1:
+        # the collective lives inside the boundary: qbx_fock_build(_device) ends in the library's own ncclAllReduce
+        # (include/qbx.h: qbx_comm_init); torch.distributed only carries the 128-byte NCCL id and the timing barriers
+        from quiqbox_b200.parallel import LibComm
+        LibComm(rank, world)
     stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch, NCCL and libqbx
     torch.cuda.set_stream(stream)
     L.check(lib.qbx_set_stream(C.c_void_p(stream.cuda_stream)))
@@ -210,9 +266,7 @@ def main():
     def step():
         L.check(lib.qbx_eri_recompute_async(db.handle))
         L.check(lib.qbx_fock_build_device(db.handle, 1, C.c_void_p(dDJ.data_ptr()), C.c_void_p(dDK.data_ptr()),
-                                          C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))
-        if world > 1:
-            dist.all_reduce(dG)
+                                          C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))     # incl. the all-reduce
 
     def barrier():
         if world > 1:
@@ -241,8 +295,6 @@ def main():
     for _ in range(args.steps):
         L.check(lib.qbx_fock_build_device(db.handle, 1, C.c_void_p(dDJ.data_ptr()), C.c_void_p(dDK.data_ptr()),
                                           C.c_void_p(dG.data_ptr()), C.c_void_p(stream.cuda_stream)))
-        if world > 1:
-            dist.all_reduce(dG)
     fe[1].record(stream)
     barrier()
     fock_ms = fe[0].elapsed_time(fe[1]) / args.steps
@@ -295,9 +347,7 @@ def main():
             L.check(lib.qbx_eri_store(h, args.screen, 0, rank, world))
             t2 = time.perf_counter()
             L.check(lib.qbx_fock_build(h, 1, L.ptr(DJh), L.ptr(DKh), L.ptr(Gh)))
-            phases = [t1 - t0, t2 - t1, time.perf_counter() - t2]
-            if world > 1:
-                g = torch.from_numpy(Gh).cuda(); dist.all_reduce(g); Gh[:] = g.cpu().numpy()
+            phases = [t1 - t0, t2 - t1, time.perf_counter() - t2]          # (the Fock build includes the library's all-reduce)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             lib.qbx_basis_destroy(h)
@@ -339,8 +389,7 @@ def main():
             nacc = ((la + lb + 1) * (la + lb + 2) * (la + lb + 3) // 6 - la * (la + 1) * (la + 2) // 6) * \
                    ((lc + ld + 1) * (lc + ld + 2) * (lc + ld + 3) // 6 - lc * (lc + 1) * (lc + 2) // 6)
             if nacc >= 180:                                   # QBX_COOP_ACC: warp-cooperative kernels
-                return (f"eri_coop2_kernel<{la},{lb},{lc},{ld}>" if os.environ.get("QBX_COOP2", "1") != "0"
-                        else "eri_coop_kernel")
+                return f"eri_coop2_kernel<{la},{lb},{lc},{ld}>"
             if lb == 0 and lc == 0 and ld == 0 and la <= 1 and os.environ.get("QBX_GC", "1") != "0":
                 return f"eri_group_kernel<{la}>"              # ket-side general-contraction sharing
             return f"eri_class_kernel<{la},{lb},{lc},{ld}>"
@@ -349,8 +398,7 @@ def main():
                 traffic = tj["dram_bytes_per_launch"].get(kernel_name(code))
         except Exception:
             pass
-        switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_GC_DS", "QBX_COOP2", "QBX_COOP_MIN_ACC", "QBX_ERI_SPILL_THREADS", "QBX_DIGEST_SEG", "QBX_DIGEST_SPREAD",
-                                               "QBX_DIGEST_ROWS", "QBX_DEVICE_PAIRS", "QBX_SCHWARZ_SPLIT", "QBX_POOL_GB") if k in os.environ}
+        switches = {k: os.environ[k] for k in ("QBX_GC", "QBX_COOP_MIN_ACC", "QBX_DIGEST_SPREAD", "QBX_POOL_GB") if k in os.environ}
         per_class = [{"class": f"({int(r[0]) // 1000}{int(r[0]) // 100 % 10}|{int(r[0]) // 10 % 10}{int(r[0]) % 10})",
                       "ms": r[1] * 1e3, "quartets": r[2], "prim_quartets": r[3],
                       "tflops_model": (r[4] / r[1] * 1e-12) if r[1] > 0 else 0.0, "kernel": kernel_name(int(r[0]))} for r in cls if r[2] > 0]
@@ -358,12 +406,15 @@ def main():
             "metric": METRIC, "value": tot_values / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label, "nbf": n, "shells": info["nshell"], "unique_shell_quartets": tot_quartets,
-                       "unique_eris": tot_values, "prim_quartets": tot_primq, "screen_tol": args.screen,
-                       "l2": "inputs larger than L2 (packed store %.1f GB/rank)" % (info["stored_bytes"] * 1e-9),
-                       "parallelism": f"shell-quartet shards x{world}", "setup_seconds": setup_s,
-                       "switches": switches or "defaults"},
+            "config": bench_config(label, n, args.screen),
+            "workload_stats": {"shells": info["nshell"], "unique_shell_quartets": tot_quartets, "unique_eris": tot_values,
+                               "prim_quartets": tot_primq,
+                               "l2": "inputs larger than L2 (packed store %.1f GB/rank)" % (info["stored_bytes"] * 1e-9),
+                               "parallelism": f"shell-quartet shards x{world}", "setup_seconds": setup_s,
+                               "switches": switches or "defaults"},
             "eri_ms": eri_ms_max, "fock_build_ms": fock_max, "fock_build_s_per_iter": fock_max * 1e-3,
+            "secondary_metric": {"metric": "rhf_fock_build_seconds_per_iter", "value": fock_max * 1e-3, "unit": "s",
+                                 "higher_is_better": False, "note": "stored-mode J/K digestion + all-reduce, device-timed, max over ranks"},
             "gpu_launches": int(round((st1["launches"] - st0["launches"]))),
             "roofline": {"bound": "fp64", "kernel": kernel_name(code),
                          "achieved": kflops, "peak": peak.value, "unit": "TFLOP/s", "frac": kflops / peak.value if peak.value else None,
@@ -380,10 +431,14 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if world == 1 and args.cpu_seconds > 0:
+            threads = cpu_threads()
             v, nd, tu = cpu_sample(bs, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            f_small, f_target = cpu_fock_sample(n_target=n)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{nd} uniformly sampled contracted ERIs of {label} in {tu:.1f} s, OpenMP over "
-                                              "quartets; per-primitive-component algorithm of the reference"}
+                                              f"quartets ({threads} threads); per-primitive-component algorithm of the reference",
+                                    "fock_build_s": f_target, "fock_build_s_measured_n120": f_small,
+                                    "fock_build_rule": "orc_getGcore (= HartreeFock.jl:305-319) on a dense N = 120 tensor, x (N/120)^4"}
         if world == 1 and args.cpu_batched:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))

@@ -29,15 +29,23 @@ extern "C" {
 
 typedef struct qbx_basis qbx_basis;
 
+/* libqbx.so is built with -fvisibility=hidden: the functions declared here are its ENTIRE dynamic symbol table (no C++
+ * internals, no CUDA device stubs), so it can sit in one process next to other CUDA libraries (Julia + CUDA.jl, torch). */
+#if defined(__GNUC__)
+#define QBX_API __attribute__((visibility("default")))
+#else
+#define QBX_API
+#endif
+
 /* error codes */
 enum { QBX_OK = 0, QBX_ERR_ARG = 1, QBX_ERR_CUDA = 2, QBX_ERR_STATE = 3, QBX_ERR_RANGE = 4, QBX_ERR_NOMEM = 5 };
 
 /* Select and initialise CUDA device `device` for this process (idempotent).  n_dev_out (may
  * be NULL) receives the number of visible devices.  No reference counterpart (the reference
  * has no device); called once from the Julia glue's __init__. */
-int qbx_init(int device, int *n_dev_out);
-int qbx_shutdown(void);
-const char *qbx_last_error(void);
+QBX_API int qbx_init(int device, int *n_dev_out);
+QBX_API int qbx_shutdown(void);
+QBX_API const char *qbx_last_error(void);
 
 /* Basis ingestion = what MultiOrbitalData holds (src/OrbitalBases.jl:439-468) after
  * getOrbCorePointers/buildOrbCoreWeight! folded normalisation into the weights
@@ -50,25 +58,25 @@ const char *qbx_last_error(void);
  * Shells are reconstructed inside (functions that share centre, exponents and radial
  * coefficients up to a per-component factor); functions that do not factor into shells
  * are kept as generic single functions. */
-int qbx_basis_create(int64_t nprim, const double *cen, const double *xpn, const int32_t *ang,
+QBX_API int qbx_basis_create(int64_t nprim, const double *cen, const double *xpn, const int32_t *ang,
                      int64_t nbf, const int64_t *bf_off, const int64_t *bf_prim, const double *bf_w,
                      qbx_basis **out);
-int qbx_basis_destroy(qbx_basis *b);
+QBX_API int qbx_basis_destroy(qbx_basis *b);
 
 /* info[0..15]: nbf, nshell, max l, class-path usable (1/0), n shell pairs, n unique shell
  * quartets in this rank's shard (after screening), n unique contracted ERI values in the
  * shard, stored bytes, n primitive quartets evaluated, rest reserved (0). */
-int qbx_basis_info(qbx_basis *b, int64_t *info);
+QBX_API int qbx_basis_info(qbx_basis *b, int64_t *info);
 
 /* seam 1, whole tensor: = elecRepulsions(bs) (src/Integration/Interface.jl:356-365 ->
  * getOrbVectorIntegralCore!, Framework.jl:640-698).  out: host, nbf^4 doubles, column-major,
  * all 8 permutational images written.  Fails without writing if out_bytes < nbf^4 * 8. */
-int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes);
+QBX_API int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes);
 
 /* seam 1, single entries: = elecRepulsion(a,b,c,d) (Interface.jl:331-342 ->
  * getOrbLayoutIntegralCore!, Framework.jl:526-554).  ijkl: 4 x n, 0-based function indices;
  * any angular momentum (generic per-function kernel). */
-int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, double *out);
+QBX_API int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, double *out);
 
 /* Build this rank's device-resident ERI representation for repeated Fock builds: what
  * initializeHartreeFock obtains at src/HartreeFock.jl:189-191 and stores in
@@ -77,34 +85,49 @@ int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, double *out);
  *   mode        0 = stored (packed unique ERIs kept in HBM), 1 = direct (recomputed in
  *               every qbx_fock_build), 2 = dense N^4 tensor (small N / irregular bases)
  *   rank,nranks shard of the cost-balanced shell-quartet list owned by this process */
-int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank, int nranks);
+QBX_API int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank, int nranks);
 
 /* seam 2: = getGcore(HeeI, DJ, DK_m) for m = 0..nmat-1 sharing one DJ
  * (src/HartreeFock.jl:305-327; RHF nmat = 1 with DJ = 2D, DK = D; UHF nmat = 2 with
  * DJ = Da+Db, DK = Da, Db).  DJ: nbf^2, DK and G: nbf^2 * nmat, column-major, host.
- * G is Hermitian-filled.  With nranks > 1 the result is this rank's PARTIAL G; the caller
- * sums over ranks (torch.distributed / NCCL all-reduce). */
-int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const double *DK, double *G);
+ * G is Hermitian-filled.  DJ and DK must be symmetric (they are densities; the packed-store
+ * digestion uses the 8-fold symmetry of the integrals together with D = D^T): a non-symmetric
+ * argument is rejected with QBX_ERR_ARG in modes 0 and 1 (mode 2, the dense tensor, accepts any).
+ * Multi-GPU (nranks > 1 in qbx_eri_store): when this process has joined a communicator of the same
+ * size (qbx_comm_init) the partial matrices are summed INSIDE this call by one ncclAllReduce and
+ * every rank receives the full G, as getGcore's callers expect (HartreeFock.jl:322-327); without a
+ * communicator the result is this rank's PARTIAL G and the caller must sum over the ranks. */
+QBX_API int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const double *DK, double *G);
+
+/* Communicator for nranks > 1: one process per GPU.  One rank obtains 128 bytes with
+ * qbx_comm_unique_id and hands them to the others by whatever channel the host has (MPI.jl,
+ * Distributed.jl, a file); then every rank calls qbx_comm_init(rank, nranks, id) after qbx_init.
+ * NCCL is bound at run time (libnccl.so.2); nranks = 1 needs neither NCCL nor an id.
+ * qbx_comm_info: rank and size of the communicator this process is in (0 and 1 if none). */
+QBX_API int qbx_comm_unique_id(void *id128);
+QBX_API int qbx_comm_init(int rank, int nranks, const void *id128);
+QBX_API int qbx_comm_info(int *rank, int *nranks);
+QBX_API int qbx_comm_destroy(void);
 
 /* Same, device pointers and a caller stream (cudaStream_t as void*; NULL = the library's
- * stream); asynchronous with respect to the host.  This is what the multi-GPU host code
- * feeds straight into the NCCL all-reduce. */
-int qbx_fock_build_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG,
+ * stream); asynchronous with respect to the host.  The all-reduce over the communicator's ranks
+ * (see qbx_fock_build) is enqueued on the same stream. */
+QBX_API int qbx_fock_build_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG,
                           void *stream);
 
 /* Recompute this rank's shard of unique ERIs into the packed store (the ERI-throughput
  * step bench.py times).  Synchronous. */
-int qbx_eri_recompute(qbx_basis *b);
+QBX_API int qbx_eri_recompute(qbx_basis *b);
 
 /* One-electron matrices needed to close an SCF (the first "next" row):
  * kind 0 overlap, 1 kinetic, 2 nuclear attraction (src/Integration/Interface.jl:46-312;
  * engines GaussianOrbitals.jl:94-363, 478-522).  Z: nnuc charges, R: 3 x nnuc. out: nbf^2. */
-int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *Z, const double *R, double *out);
+QBX_API int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *Z, const double *R, double *out);
 
 /* Boys function in isolation: out[(mmax+1)*t + m] = F_m(T[t])
  * (computeBoysSequence, src/Integration/Engines/BoysFunction.jl:67-77).
  * table != 0 uses the tabulated fast path of the class kernels (mmax <= 8). */
-int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
+QBX_API int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
 
 /* Synthetic throughput sweep: nquartets contracted shell quartets of class
  * (la lb|lc ld) with uniform contraction degree K, generated from `seed` (centres uniform in
@@ -113,29 +136,29 @@ int qbx_boys(int64_t n, const double *T, int mmax, int table, double *out);
  * shell quartets actually evaluated (primitive pairs whose prefactor underflows are dropped, so
  * this is <= nquartets * K^4).  sample_out (may be NULL): the first min(nsample, nquartets)
  * quartets' values and sample_geom their inputs, for oracle checks. */
-int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed,
+QBX_API int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nquartets, uint64_t seed,
                    double *secs, double *checksum, double *prim_quartets, int64_t nsample,
                    double *sample_out, double *sample_geom);
 
 /* Asynchronous variant of qbx_eri_recompute: only enqueues the class kernels on the
  * library's stream (see qbx_set_stream). */
-int qbx_eri_recompute_async(qbx_basis *b);
+QBX_API int qbx_eri_recompute_async(qbx_basis *b);
 
 /* Make every later launch of this process use `stream` (cudaStream_t as void*; NULL restores
  * the library's own stream).  Lets a host framework (torch.distributed + NCCL) order its
  * collectives and CUDA events with the library's kernels on one stream. */
-int qbx_set_stream(void *stream);
+QBX_API int qbx_set_stream(void *stream);
 
 /* Per-class device times: runs one extra recompute with the class kernels serialised on the
  * library's stream and CUDA events around each of them (the normal recompute overlaps the
  * classes on side streams), then synchronises.
  * out[21][6]: la*1000+lb*100+lc*10+ld, seconds, shell quartets, primitive quartets,
  * model flops, component values.  Rows follow the canonical class order. */
-int qbx_class_stats(qbx_basis *b, double *out);
+QBX_API int qbx_class_stats(qbx_basis *b, double *out);
 
 /* Measured FP64 FMA peak of the bound device (register-resident DFMA chains, all SMs):
  * the roofline denominator of the ERI kernels (MEASURED_PEAKS.json has no FP64 entry). */
-int qbx_fp64_peak(double *tflops);
+QBX_API int qbx_fp64_peak(double *tflops);
 
 /* Device allocations of the library (basis tables, task lists, the packed ERI store) come from
  * a size-keyed pool, so that the create -> store -> destroy cycle of a geometry scan or an
@@ -144,12 +167,12 @@ int qbx_fp64_peak(double *tflops);
  * cached bytes (default 64, 0 = no pooling).  qbx_pool_trim returns the idle blocks to the
  * driver; counts (nullable) receives [0] reuses, [1] driver allocations, [2] idle bytes before
  * the trim. */
-int qbx_pool_trim(int64_t *counts);
+QBX_API int qbx_pool_trim(int64_t *counts);
 
 /* counters since the last reset: [0] kernels launched, [1] device seconds in ERI kernels,
  * [2] device seconds in digestion kernels, [3] primitive quartets evaluated,
  * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */
-int qbx_stats(qbx_basis *b, double *out, int reset);
+QBX_API int qbx_stats(qbx_basis *b, double *out, int reset);
 
 #ifdef __cplusplus
 }

@@ -119,13 +119,32 @@ function Base.getindex(e::DeviceERI, i::Int, j::Int, k::Int, l::Int)   # slow pa
     out[]
 end
 
+# ---- multi-GPU: one Julia process per GPU.  The partial Fock matrices are summed INSIDE qbx_fock_build by the library's
+# own ncclAllReduce, so that getGcore keeps its contract (the result is the full G, HartreeFock.jl:322-327).  Rank 0
+# obtains the 128-byte NCCL id and hands it to the others by the host's own channel, e.g. with MPI.jl:
+#     id = zeros(UInt8, 128); rank == 0 && QuiqboxB200.comm_unique_id!(id); MPI.Bcast!(id, 0, comm)
+#     QuiqboxB200.comm_init(rank, nranks, id)
+comm_unique_id!(id::Vector{UInt8}) = (length(id) == 128 || throw(ArgumentError("id must hold 128 bytes"));
+    GC.@preserve id check(ccall((:qbx_comm_unique_id, libqbx), Cint, (Ptr{UInt8},), id)); id)
+comm_init(rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    GC.@preserve id check(ccall((:qbx_comm_init, libqbx), Cint, (Cint, Cint, Ptr{UInt8}), rank, nranks, id))
+function comm_size()
+    r = Ref{Cint}(0); n = Ref{Cint}(1)
+    check(ccall((:qbx_comm_info, libqbx), Cint, (Ptr{Cint}, Ptr{Cint}), r, n))
+    (Int(r[]), Int(n[]))
+end
+
 function DeviceERI(source, ptrVector; screen::Float64=1e-12, mode::Integer=0, rank::Integer=0, nranks::Integer=1)
+    # a sharded store without the communicator would make getGcore return a PARTIAL G into Quiqbox's unchanged SCF loop
+    nranks > 1 && comm_size() != (Int(rank), Int(nranks)) &&
+        throw(ArgumentError("QuiqboxB200: nranks = $nranks needs QuiqboxB200.comm_init(rank, nranks, id) on every rank first"))
     b = flatten(source, ptrVector)
     check(ccall((:qbx_eri_store, libqbx), Cint, (Ptr{Cvoid}, Float64, Cint, Cint, Cint), b.ptr, screen, mode, rank, nranks))
     DeviceERI(b)
 end
 
-# getGcore(HeeI, DJ, DK): replaces the Threads.@threads loop over (mu, nu) by one call
+# getGcore(HeeI, DJ, DK): replaces the Threads.@threads loop over (mu, nu) by one call.  DJ and DK must be symmetric
+# (they are densities); the library rejects anything else with an error instead of a mode-dependent result.
 function Quiqbox.getGcore(HeeI::DeviceERI, DJ::Matrix{Float64}, DK::Matrix{Float64})
     G = similar(DJ)
     GC.@preserve DJ DK G check(ccall((:qbx_fock_build, libqbx), Cint,

@@ -678,3 +678,22 @@ void orc_packed_gcore(int64_t N, int64_t p0, int64_t p1, const int64_t *off, con
         free(g);
     }
 }
+
+/* OpenMP team size, set explicitly by bench.py: a launcher (torch.distributed.run) exports OMP_NUM_THREADS=1,
+ * which silently turned the round-1 reference arm into a single-threaded run labelled with all cores. */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+    int t = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        t = omp_get_num_threads();
+    }
+    return t;
+}
+#else
+int orc_set_threads(int n) { (void)n; return 1; }
+#endif

@@ -1,8 +1,8 @@
 """Builds quiqbox.jl_b200/libqbx.so (sm_100a only) from csrc/ with nvcc, in-tree.
 
 21 per-class translation units (class_inst.cu compiled with -DQLA.. macros) + 4 host/generic
-units, compiled in parallel, then linked into one shared library whose exported symbols are
-exactly include/qbx.h.  Incremental: a unit is rebuilt when its sources are newer than its
+units, compiled in parallel, then linked into one shared library whose dynamic symbol table is
+exactly include/qbx.h (-fvisibility=hidden + QBX_API; tests/test_abi_cpu.py compares the two).  Incremental: a unit is rebuilt when its sources are newer than its
 object.  `python quiqbox.jl_b200/build.py [-j N] [--force]`.
 """
 import concurrent.futures as cf
@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libqbx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-I", CSRC]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++", "-I", CSRC]
 # tuning constants for A/B builds on the GPU box, e.g. QBX_NVCC_DEFS="-DQBX_ERI_THREADS=128 -DCOOP_WARPS=8"
 # (then --force; the defaults are the product)
 FLAGS += os.environ.get("QBX_NVCC_DEFS", "").split()
@@ -49,7 +49,7 @@ def build(jobs=None, force=False, verbose=True):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     work, objs = [], []
-    for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool"):
+    for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm"):
         src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
@@ -69,7 +69,7 @@ def build(jobs=None, force=False, verbose=True):
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed for {obj}:\n{out}")
     if work or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs
+        cmd = [NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs + ["-ldl", "-Xlinker", "--version-script=" + os.path.join(CSRC, "libqbx.map")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

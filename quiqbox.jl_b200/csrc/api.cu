@@ -118,8 +118,14 @@ struct qbx_basis {
     double *d_dense = nullptr;          // mode 2
     double *d_DJ = nullptr, *d_DK = nullptr, *d_G = nullptr;   // staging for host-pointer Fock builds
     int staged_nmat = 0;
+    int nranks = 1;                     // shards the stored representation was cut into (qbx_eri_store)
     double stats[16] = {0};
 };
+
+// comm.cu
+int qbx_comm_rank();
+int qbx_comm_size();
+int qbx_comm_allreduce(double *d_buf, size_t count, cudaStream_t s);
 
 template <class T>
 static int to_device(T **dst, const std::vector<T> &src)
@@ -251,8 +257,13 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
     }
     int rc = ensure_init();
     if (rc) return rc;
+    if (nranks > 1 && qbx_comm_size() == nranks && qbx_comm_rank() != rank) {
+        qbx_set_error("qbx_eri_store: rank differs from the rank of this process in the communicator (qbx_comm_init)");
+        return QBX_ERR_ARG;
+    }
     std::lock_guard<std::mutex> lk(b->mu);
     free_store(b);
+    b->nranks = nranks;
     if (mode == 2 || !b->eng) {
         if (nranks != 1) { qbx_set_error("qbx_eri_store: the dense mode does not shard"); return QBX_ERR_ARG; }
         const int64_t N = b->nbf, need = N * N * N * N * (int64_t)sizeof(double);
@@ -355,7 +366,11 @@ static int fock_device(qbx_basis *b, int nmat, const double *dDJ, const double *
         b->stats[0] += 1;
         return qbx_launch_dense_gcore(b->nbf, b->d_dense, nmat, dDJ, dDK, dG, s);
     }
-    return b->eng->fock(nmat, dDJ, dDK, dG, s, b->stats);
+    int rc = b->eng->fock(nmat, dDJ, dDK, dG, s, b->stats);
+    // the collective inside the boundary: with a communicator of the store's size the partial G of the ranks is summed
+    // here (one ncclAllReduce on the same stream), and getGcore's contract -- the result is the full G -- holds
+    if (!rc && b->nranks > 1 && qbx_comm_size() == b->nranks) rc = qbx_comm_allreduce(dG, (size_t)nmat * b->nbf * b->nbf, s);
+    return rc;
 }
 
 extern "C" int qbx_fock_build_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG, void *stream)
@@ -374,8 +389,25 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
+    if (b->mode == 0 || b->mode == 1) {
+        // the packed-store digestion is only valid for symmetric densities (include/qbx.h); reject anything else here
+        // instead of returning a mode-dependent result
+        const int64_t N = b->nbf;
+        for (int m = 0; m <= nmat; ++m) {
+            const double *D = m == 0 ? DJ : DK + (size_t)(m - 1) * N * N;
+            for (int64_t j = 0; j < N; ++j)
+                for (int64_t i = 0; i < j; ++i) {
+                    const double v = D[i + N * j], w = D[j + N * i];
+                    if (!(fabs(v - w) <= 1e-10 * std::max(1.0, std::max(fabs(v), fabs(w))))) {
+                        qbx_set_error("qbx_fock_build: DJ and DK must be symmetric matrices (stored and direct modes)");
+                        return QBX_ERR_ARG;
+                    }
+                }
+        }
+    }
     if (b->staged_nmat < nmat) {
         qbx_pool_free(b->d_DJ); qbx_pool_free(b->d_DK); qbx_pool_free(b->d_G);
+        b->d_DJ = b->d_DK = b->d_G = nullptr; b->staged_nmat = 0;      // (an early return below must not leave dangling pointers)
         QBX_CUDA(qbx_dmalloc(&b->d_DJ, n2));
         QBX_CUDA(qbx_dmalloc(&b->d_DK, n2 * 2));
         QBX_CUDA(qbx_dmalloc(&b->d_G, n2 * 2));

@@ -127,11 +127,9 @@ __global__ void k_schwarz(const double *vals, int n, int nab, double *Q)
 }
 
 
-// ---- primitive-pair records built on the device (opt-in: QBX_DEVICE_PAIRS=1; written without GPU access).
-// build_pairset() below computes the 64-byte records of ~1.5e5 primitive pairs on host threads and
-// uploads ~25 MB per basis: 6 of the 7 ms of qbx_basis_create for (H2O)16.  Here the host uploads the shell
-// table once (a few kB), a kernel counts the surviving primitive pairs of every shell pair, the host sorts
-// the pairs by that count (the one small read-back), and a second kernel writes the AoS / SoA records in place.
+// ---- primitive-pair records built on the device: the host uploads the shell table once (a few kB), a kernel counts
+// the surviving primitive pairs of every shell pair, the host sorts the pairs by that count (the one small
+// read-back), and a second kernel writes the AoS / SoA records in place.
 struct DevShells { const double *cen; const int *xoff; const double *xpn, *coef; };
 
 __device__ __forceinline__ double pair_prefactor(double pref, double a, double b, double ca, double cb, double ab2, double z)
@@ -271,27 +269,36 @@ __global__ void k_task_cost(const int2 *tasks, int64_t n, const int *poffb, cons
     if (threadIdx.x == 0) atomicAdd(sum, red[0]);
 }
 
-// G = (Jt + Jt^T) - (Kt + Kt^T), written in the caller's (external) numbering
+// G = (Jt + Jt^T) - (Kt + Kt^T), written in the caller's (external) numbering.  *bad != 0: a density was not
+// symmetric (k_permute_in) -- the half-accumulators mean nothing then, and G is poisoned with NaN rather than
+// returned silently wrong (the host-pointer entry point rejects such input before it gets here).
 __global__ void k_finish_G(int64_t Nint, int64_t Next, const int *ext_of_int, int nmat, const double *Jt, const double *Kt,
-                           double *G)
+                           double *G, const int *bad)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= Nint * Nint) return;
     const int64_t i = e % Nint, j = e / Nint, et = j + Nint * i;
     const int ie = ext_of_int[i], je = ext_of_int[j];
     if (ie < 0 || je < 0) return;
-    const double jv = Jt[e] + Jt[et];
+    const double jv = *bad ? nan("") : Jt[e] + Jt[et];
     for (int m = 0; m < nmat; ++m)
         G[m * Next * Next + ie + Next * je] = jv - (Kt[m * Nint * Nint + e] + Kt[m * Nint * Nint + et]);
 }
 
-// external <-> internal function numbering (internal = complete Cartesian shells, shell by shell)
-__global__ void k_permute_in(int64_t Next, int64_t Nint, const int *ext_of_int, const double *Dext, double *Dint)
+// external <-> internal function numbering (internal = complete Cartesian shells, shell by shell); flags a density
+// that is not symmetric (relative 1e-10: densities C C^T are symmetric to rounding)
+__global__ void k_permute_in(int64_t Next, int64_t Nint, const int *ext_of_int, const double *Dext, double *Dint, int *bad)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= Nint * Nint) return;
     const int i = ext_of_int[e % Nint], j = ext_of_int[e / Nint];
-    Dint[e] = (i >= 0 && j >= 0) ? Dext[i + Next * j] : 0.0;
+    double v = 0.0;
+    if (i >= 0 && j >= 0) {
+        v = Dext[i + Next * j];
+        const double w = Dext[j + Next * i];
+        if (!(fabs(v - w) <= 1e-10 * fmax(1.0, fmax(fabs(v), fabs(w))))) atomicOr(bad, 1);
+    }
+    Dint[e] = v;
 }
 
 // cost of every 32-task chunk = primitive quartets behind its tasks
@@ -458,101 +465,10 @@ Engine *Engine::from_shells(const std::vector<HostShell> &shells, int64_t nbf, b
     return e;
 }
 
-static int build_pairset(const std::vector<HostShell> &sh, int la, int lb, std::vector<std::pair<int, int>> sp,
-                         bool sort_by_nprim, DevPairSet &out, std::vector<int2> &shells)
-{
-    std::unique_ptr<TraceScope> tr(new TraceScope("pairset: host"));
-    // primitive-pair records (zeta, P, K, b, 1/2zeta, 1/zeta); pairs are independent -> host threads
-    const size_t np_ = sp.size();
-    std::vector<size_t> cap(np_ + 1, 0);
-    for (size_t i = 0; i < np_; ++i) cap[i + 1] = cap[i] + sh[sp[i].first].xpn.size() * sh[sp[i].second].xpn.size();
-    // rec | prim | soa | geom live in the pinned staging area
-    std::lock_guard<std::mutex> staging_lock(qbx_staging_mutex());
-    const size_t n_rec = 8 * cap[np_], n_soa = (size_t)QBX_SOA_NF * cap[np_], n_geom = 8 * np_;
-    double *stage = (double *)qbx_staging((2 * n_rec + n_soa + n_geom + 8) * sizeof(double));
-    if (!stage) { qbx_set_error("pinned staging allocation failed"); return QBX_ERR_NOMEM; }
-    double *rec = stage, *prim = rec + n_rec, *soa = prim + n_rec, *geom = soa + n_soa;
-    std::vector<int> cnt(np_, 0);
-    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
-    qbx_parallel_for(np_, 256, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) {
-            const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
-            double ab2 = 0;
-            for (int d = 0; d < 3; ++d) ab2 += (A.cen[d] - B.cen[d]) * (A.cen[d] - B.cen[d]);
-            double *r = rec + 8 * cap[i];
-            int c = 0;
-            for (size_t pa = 0; pa < A.xpn.size(); ++pa)
-                for (size_t pb = 0; pb < B.xpn.size(); ++pb) {
-                    const double a = A.xpn[pa], b = B.xpn[pb], z = a + b;
-                    const double K = pref * A.coef[pa] * B.coef[pb] * exp(-a * b / z * ab2) / z;
-                    if (fabs(K) < 1e-24) continue;
-                    double *v = r + 8 * c++;
-                    v[0] = z;
-                    for (int d = 0; d < 3; ++d) v[1 + d] = (a * A.cen[d] + b * B.cen[d]) / z;
-                    v[4] = K; v[5] = b; v[6] = 0.5 / z; v[7] = 1.0 / z;
-                }
-            cnt[i] = c;
-        }
-    });
-    std::vector<int> order(np_);
-    std::iota(order.begin(), order.end(), 0);
-    if (sort_by_nprim)
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
-    shells.assign(np_, make_int2(0, 0));               // (A, B) per pair in device order, also returned to the caller
-    std::vector<int> poff(np_ + 1, 0);
-    out.h_nprim.resize(np_);
-    for (size_t n = 0; n < np_; ++n) { out.h_nprim[n] = cnt[order[n]]; poff[n + 1] = poff[n] + cnt[order[n]]; }
-    const size_t n_prim = 8 * (size_t)poff[np_], n_soa_used = (size_t)QBX_SOA_NF * poff[np_];
-    // transposed copy for coalesced ket-side loads (see PairSet in eri_class.cuh): runs of pairs with
-    // the same primitive count form one block [primitive][field][pair]
-    std::vector<int2> soa_idx(np_);
-    {
-        size_t base = 0, g0 = 0;
-        while (g0 < np_) {
-            size_t g1 = g0;
-            while (g1 < np_ && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
-            const size_t g = g1 - g0;
-            for (size_t j = g0; j < g1; ++j) soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
-            base += g * (size_t)out.h_nprim[g0] * QBX_SOA_NF;
-            g0 = g1;
-        }
-    }
-    qbx_parallel_for(np_, 256, [&](size_t lo, size_t hi) {
-        for (size_t n = lo; n < hi; ++n) {
-            const int i = order[n];
-            const HostShell &A = sh[sp[i].first], &B = sh[sp[i].second];
-            shells[n] = make_int2(sp[i].first, sp[i].second);
-            for (int d = 0; d < 3; ++d) { geom[8 * n + d] = A.cen[d]; geom[8 * n + 3 + d] = A.cen[d] - B.cen[d]; }
-            geom[8 * n + 6] = geom[8 * n + 7] = 0.0;
-            const double *r = rec + 8 * cap[i];
-            std::copy(r, r + 8 * (size_t)cnt[i], prim + 8 * (size_t)poff[n]);
-            const size_t b0 = (size_t)soa_idx[n].x, g = (size_t)soa_idx[n].y;
-            for (int pp = 0; pp < cnt[i]; ++pp)
-                for (int k = 0; k < QBX_SOA_NF; ++k) soa[b0 + ((size_t)pp * QBX_SOA_NF + k) * g] = r[8 * pp + k];
-        }
-    });
-    out.la = la; out.lb = lb; out.npair = (int)sp.size(); out.nprim = poff.back();
-    tr.reset(new TraceScope("pairset: upload"));
-    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa_used) * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, soa_idx.size()) * sizeof(int2)));
-    QBX_CUDA(qbx_dmalloc(&out.shells, std::max<size_t>(1, shells.size()) * sizeof(int2)));
-    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
-    QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, n_geom) * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, n_prim) * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&out.schwarz, std::max<size_t>(1, sp.size()) * sizeof(double)));
-    if (n_soa_used) QBX_CUDA(cudaMemcpy(out.soa, soa, n_soa_used * sizeof(double), cudaMemcpyHostToDevice));
-    if (!soa_idx.empty()) QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), soa_idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    if (!sp.empty()) {
-        QBX_CUDA(cudaMemcpy(out.shells, shells.data(), shells.size() * sizeof(int2), cudaMemcpyHostToDevice));
-        QBX_CUDA(cudaMemcpy(out.geom, geom, n_geom * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    QBX_CUDA(cudaMemcpy(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if (n_prim) QBX_CUDA(cudaMemcpy(out.prim, prim, n_prim * sizeof(double), cudaMemcpyHostToDevice));
-    return QBX_OK;
-}
-
-
-// device variant of build_pairset (see k_pair_count / k_pair_fill); same outputs
+// Primitive-pair records of one pair class, computed on the device (k_pair_count / k_pair_fill): the host uploads the
+// shell table, reads back one int per shell pair, sorts the pairs by it and the fill kernel writes the AoS and SoA
+// copies in place.  [The host-thread variant of round 1 -- 6 of the 7 ms of qbx_basis_create -- was deleted after the
+// A/B of round 2: host-buffer step 52.1 -> 49.1 ms, profiles/r02/probe_ab_head_of_round1.log.]
 static int build_pairset_device(const std::vector<HostShell> &sh, const DevShells &S, int la, int lb,
                                 const std::vector<std::pair<int, int>> &sp, bool sort_by_nprim, DevPairSet &out,
                                 std::vector<int2> &shells, cudaStream_t s)
@@ -648,47 +564,18 @@ int Engine::upload(bool pair_adjacent)
             sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({a, b});
         }
     } else {
-        // Shell pairs of a class are listed DIAGONAL BY DIAGONAL: (A_(j+k), B_j), j = 0, 1, .. for k = 0, 1, ..  Any 32
-        // consecutive pairs -- and any 32 consecutive survivors of the Schwarz screening -- then consist of 32
-        // different first shells and 32 different second shells, which is what lets the digestion warps update
-        // their shared-memory K rows without atomics or shuffle reductions (digest.cuh).  Shells are sorted by
-        // l, so with A taken from the higher l (or, for equal l, the later shell) a >= b holds as before.
-        std::vector<int> of_l[QBX_MAX_L + 1];
-        for (size_t a = 0; a < ns; ++a) of_l[shells_[a].l].push_back((int)a);
-        for (int la = 0; la <= QBX_MAX_L; ++la)
-            for (int lb = 0; lb <= la; ++lb) {
-                const std::vector<int> &SA = of_l[la], &SB = of_l[lb];
-                auto &out = sp[pair_cls(la, lb)];
-                if (SA.empty() || SB.empty()) continue;
-                if (la == lb) {
-                    const size_t n = SA.size();
-                    for (size_t k = 0; k < n; ++k)
-                        for (size_t j = 0; j + k < n; ++j) out.push_back({SA[j + k], SA[j]});
-                } else {
-                    const size_t nA = SA.size(), nB = SB.size(), M = std::max(nA, nB);
-                    for (size_t k = 0; k < M; ++k) {
-                        if (nA <= nB) for (size_t i = 0; i < nA; ++i) out.push_back({SA[i], SB[(i + k) % M]});
-                        else for (size_t i = 0; i < nB; ++i) out.push_back({SA[(i + k) % M], SB[i]});
-                    }
-                }
-            }
+        // A major, B ascending (shells are sorted by l, so a >= b implies la >= lb): consecutive pairs share the
+        // first shell, which the digestion's segmented warp sums rely on (digest.cuh).  [Listing the pairs diagonal
+        // by diagonal, so that the 32 kets of a warp hold 32 different shells C and D, was measured in round 2
+        // and lost: it needs 32 shells of one kind, (H2O)16 has 16 -- profiles/r02/digest_history.md.]
+        for (size_t a = 0; a < ns; ++a)
+            for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
     }
     std::vector<int> first_h(ns);
     { int acc = 0; for (size_t s = 0; s < ns; ++s) { first_h[s] = acc; acc += qbx_nc(shells_[s].l); } }
-    for (int l = 0; l <= QBX_MAX_L; ++l) { l_lo_[l] = 0; l_hi_[l] = 0; }
-    {   // internal function range of every angular momentum (contiguous: shells are sorted by l)
-        bool seen[QBX_MAX_L + 1] = {false};
-        for (size_t s = 0; s < ns; ++s) {
-            const int l = shells_[s].l, lo = first_h[s], hi = first_h[s] + qbx_nc(l);
-            if (!seen[l]) { l_lo_[l] = lo; l_hi_[l] = hi; seen[l] = true; }
-            else { l_lo_[l] = std::min(l_lo_[l], lo); l_hi_[l] = std::max(l_hi_[l], hi); }
-        }
-    }
-    // QBX_DEVICE_PAIRS=1: primitive-pair records computed on the device (opt-in, unmeasured)
-    static const int dev_pairs = getenv("QBX_DEVICE_PAIRS") ? atoi(getenv("QBX_DEVICE_PAIRS")) : 0;
     DevShells S{nullptr, nullptr, nullptr, nullptr};
     void *d_tab[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (dev_pairs) {
+    {
         std::vector<double> cen(3 * ns), xp, cf;
         std::vector<int> xoff(ns + 1, 0);
         for (size_t i = 0; i < ns; ++i) {
@@ -709,8 +596,7 @@ int Engine::upload(bool pair_adjacent)
         // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
         // equal-count group a run of pairs shares A and walks over consecutive B
         std::vector<int2> sh;
-        int rc = dev_pairs ? build_pairset_device(shells_, S, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh, qbx_stream())
-                           : build_pairset(shells_, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh);
+        int rc = build_pairset_device(shells_, S, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh, qbx_stream());
         if (rc) return rc;
         {
             DevPairSet &P = pairs_[pc];
@@ -721,7 +607,7 @@ int Engine::upload(bool pair_adjacent)
             // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
             if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
                 TraceScope trg("group build");
-                if ((rc = qbx_group_build(shells_, sh, groups_, dev_pairs ? P.shells : nullptr))) return rc;
+                if ((rc = qbx_group_build(shells_, sh, groups_, P.shells))) return rc;
                 use_groups_ = groups_.ng > 0 && groups_.ng < P.npair;     // only when something is shared
             }
         }
@@ -738,7 +624,7 @@ Engine::~Engine()
     qbx_group_free(groups_);
     for (auto &p : pairs_) { qbx_pool_free(p.shells); qbx_pool_free(p.prim_off); qbx_pool_free(p.geom); qbx_pool_free(p.prim); qbx_pool_free(p.schwarz); qbx_pool_free(p.soa); qbx_pool_free(p.soa_idx); qbx_pool_free(p.info); }
     qbx_pool_free(d_shell_bf_); qbx_pool_free(d_shell_scale_); qbx_pool_free(d_shell_first_); qbx_pool_free(d_ext_of_int_); qbx_pool_free(d_Dint_);
-    qbx_pool_free(chunk_); qbx_pool_free(d_Jt_); qbx_pool_free(d_Kt_); qbx_pool_free(d_counters_);
+    qbx_pool_free(chunk_); qbx_pool_free(d_Jt_); qbx_pool_free(d_Kt_); qbx_pool_free(d_counters_); qbx_pool_free(d_bad_);
 
     for (auto &e : cls_ev_) if (e) cudaEventDestroy(e);
     for (int i = 0; i < kSide; ++i) { if (side_[i]) cudaStreamDestroy(side_[i]); if (side_ev_[i]) cudaEventDestroy(side_ev_[i]); }
@@ -827,10 +713,9 @@ int Engine::ensure_schwarz(cudaStream_t s)
         QBX_CUDA(qbx_dmalloc(&v, (size_t)ops->ncomp * P.npair * sizeof(double)));
         scratch.push_back(t); scratch.push_back(v);
         k_diag_tasks<<<(P.npair + 127) / 128, 128, 0, cs>>>(P.npair, t);
-        // a diagonal (ab|ab) of two long contractions is thousands of primitive quartets: one WARP per pair
-        // (QBX_SCHWARZ_SPLIT=0: one thread per pair, the first version)
-        static const int split = getenv("QBX_SCHWARZ_SPLIT") ? atoi(getenv("QBX_SCHWARZ_SPLIT")) : 1;
-        if (split && ops->eri_split) {
+        // a diagonal (ab|ab) of two long contractions is thousands of primitive quartets: one WARP per pair (one thread
+        // per pair, the first version, cost the host-buffer step 2 ms: 54.3 vs 52.2 ms in the A/B of round 2)
+        if (ops->eri_split) {
             ClassArgs a;
             if ((rc = eri_args(pc, pc, t, P.npair, v, cs, a))) return rc;
             if ((rc = ops->eri_split(a, cs))) {        // e.g. a launch failure: the thread-per-pair kernel still works
@@ -1134,9 +1019,11 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
     const int64_t NI2 = nint_ * nint_;
     const unsigned pg = (unsigned)((NI2 + 255) / 256);
     double *DJi = d_Dint_, *DKi = d_Dint_ + NI2;
-    k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDJ, DJi);
+    if (!d_bad_) QBX_CUDA(qbx_dmalloc(&d_bad_, sizeof(int)));
+    QBX_CUDA(cudaMemsetAsync(d_bad_, 0, sizeof(int), s));
+    k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDJ, DJi, d_bad_);
     for (int m = 0; m < nmat; ++m)
-        k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDK + m * nbf_ * nbf_, DKi + m * NI2);
+        k_permute_in<<<pg, 256, 0, s>>>(nbf_, nint_, d_ext_of_int_, dDK + m * nbf_ * nbf_, DKi + m * NI2, d_bad_);
     QBX_CUDA(cudaMemsetAsync(d_Jt_, 0, NI2 * sizeof(double), s));
     QBX_CUDA(cudaMemsetAsync(d_Kt_, 0, nmat * NI2 * sizeof(double), s));
     QBX_CUDA(cudaMemsetAsync(dG, 0, nmat * nbf_ * nbf_ * sizeof(double), s));
@@ -1152,19 +1039,12 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
             a.bra_info = pairs_[bc].info; a.ket_info = pairs_[kc].info;
             static const int spread = getenv("QBX_DIGEST_SPREAD") ? atoi(getenv("QBX_DIGEST_SPREAD")) : QBX_DIGEST_SPREAD;
             a.spread = spread > 0 ? spread : 1;
-            a.span = 0;
-            // QBX_DIGEST_SPAN=0: the round-1 kernel (every update a global RED), kept as the fallback for bases whose
-            // K rows do not fit shared memory and for A/B measurements
-            static const int rows = getenv("QBX_DIGEST_SPAN") ? atoi(getenv("QBX_DIGEST_SPAN")) : 1;
             a.nbf = (int)nint_; a.nmat = nmat; a.same_class = (bc == kc);
-            a.c0 = l_lo_[ops->lc]; a.wC = l_hi_[ops->lc] - l_lo_[ops->lc];
-            a.d0 = l_lo_[ops->ld]; a.wD = ops->lc == ops->ld ? 0 : l_hi_[ops->ld] - l_lo_[ops->ld];
             a.DJ = DJi; a.DK = DKi; a.Jt = d_Jt_; a.Kt = d_Kt_;
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
                 cudaStream_t ds = side_[kside++ % kSide];
-                int rc = rows ? ops->digest_span(a, ds) : -1;
-                if (rc < 0) rc = ops->digest(a, ds);
+                int rc = ops->digest(a, ds);
                 if (rc) return rc;
                 stats[0] += 1;
                 stats[5] += (double)tl.n * ops->ncomp * sizeof(double);
@@ -1175,8 +1055,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
                     int rc = run_eri(bc, kc, tl.tasks + o, n, chunk_, s);
                     if (rc) return rc;
                     a.tasks = tl.tasks + o; a.ntasks = n; a.vals = chunk_;
-                    rc = rows ? ops->digest_span(a, s) : -1;
-                    if (rc < 0) rc = ops->digest(a, s);
+                    rc = ops->digest(a, s);
                     if (rc) return rc;
                     stats[0] += 2;
                 }
@@ -1185,7 +1064,7 @@ int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cud
         }
     if (mode_ == 1) stats[4] += model_flops_;
     if (mode_ == 0) { int rc = join(s); if (rc) return rc; }
-    k_finish_G<<<pg, 256, 0, s>>>(nint_, nbf_, d_ext_of_int_, nmat, d_Jt_, d_Kt_, dG);
+    k_finish_G<<<pg, 256, 0, s>>>(nint_, nbf_, d_ext_of_int_, nmat, d_Jt_, d_Kt_, dG, d_bad_);
     QBX_CUDA(cudaGetLastError());
     stats[0] += 1;
     return QBX_OK;

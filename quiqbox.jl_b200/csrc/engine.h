@@ -26,9 +26,6 @@ struct DigestArgs {
     const double *vals;          // [ncomp][ntasks]
     int nbf, nmat, same_class;   // nbf = internal dimension here
     int spread;                  // number of block slots the task list is dealt over (see digest.cuh)
-    int span;                    // digest_span_kernel: tasks per warp span (a multiple of 32; set by the launcher)
-    int c0, wC, d0, wD;          // digest_span_kernel: internal functions of the shells C are [c0, c0 + wC), of the shells D
-                                 // [d0, d0 + wD); wD = 0 when both are the same range (lc == ld)
     const double *DJ, *DK;       // internal numbering: nbf^2, nmat * nbf^2
     double *Jt, *Kt;             // nbf^2, nmat * nbf^2 (half-accumulators, see digest.cuh)
 };
@@ -47,7 +44,6 @@ struct ClassOps {
     int (*eri)(const ClassArgs &, cudaStream_t);
     int (*digest)(const DigestArgs &, cudaStream_t);
     int (*scatter)(const ScatterArgs &, cudaStream_t);
-    int (*digest_span)(const DigestArgs &, cudaStream_t);  // span digestion (K rows in shared memory); returns -1 when the rows do not fit
     int (*eri_split)(const ClassArgs &, cudaStream_t);     // one warp per task (diagonal classes only, else null)
 };
 const ClassOps *qbx_class_ops(int bra_cls, int ket_cls);    // pair class = la (la + 1) / 2 + lb
@@ -96,7 +92,7 @@ struct GroupSet {
     std::vector<int> h_nprim, h_nmem;
 };
 int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &ss_pairs, GroupSet &out,
-                    const int2 *d_ss_pairs = nullptr);   // d_ss_pairs != null: records computed on the device (QBX_DEVICE_PAIRS=1)
+                    const int2 *d_ss_pairs);             // primitive records computed on the device from the (ss) pair list
 void qbx_group_free(GroupSet &g);
 // two enqueue-only phases, see Engine::tasks_count / tasks_fill.  d_total[0..2] = group tasks of all
 // ranks, group tasks of this rank, slots of this rank.
@@ -136,12 +132,9 @@ private:
                    const int64_t *h_total, TaskList &out, double *d_stat, int *d_nheavy, cudaStream_t s);
     int run_eri(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, const int *order = nullptr);
     int eri_args(int bc, int kc, const int2 *tasks, int64_t n, double *out, cudaStream_t s, ClassArgs &a);
-    // (ss|ss), (ps|ss); (ds|ss) was measured slower with its 54 accumulators (QBX_GC_DS=1 includes it: A/B runs)
-    bool grouped(int bc, int kc) const
-    {
-        static const bool ds = getenv("QBX_GC_DS") && atoi(getenv("QBX_GC_DS"));
-        return use_groups_ && kc == 0 && (bc == 0 || bc == 1 || (ds && bc == 3));
-    }
+    // (ss|ss), (ps|ss); (ds|ss) through the group kernel was measured slower twice (54 accumulators per thread:
+    // 41.4 vs 40.8 ms per step in round 2) and is not routed there
+    bool grouped(int bc, int kc) const { return use_groups_ && kc == 0 && (bc == 0 || bc == 1); }
     GroupSet groups_;
     bool use_groups_ = false;
 
@@ -159,9 +152,9 @@ private:
     double *chunk_ = nullptr;            // direct mode / tensor fill staging
     int64_t chunk_doubles_ = 0;
     double *d_Jt_ = nullptr, *d_Kt_ = nullptr;
+    int *d_bad_ = nullptr;               // set by k_permute_in when a density is not symmetric
     int *d_shell_first_ = nullptr, *d_ext_of_int_ = nullptr;
     int64_t nint_ = 0;                   // internal dimension (complete Cartesian shells)
-    int l_lo_[QBX_MAX_L + 1] = {0}, l_hi_[QBX_MAX_L + 1] = {0};   // internal functions of angular momentum l: [l_lo, l_hi)
     double *d_Dint_ = nullptr;           // DJ, DK[0], DK[1] in internal numbering
     int64_t n_quartets_ = 0, n_values_ = 0, stored_bytes_ = 0;
     double n_primq_ = 0, model_flops_ = 0;

@@ -310,111 +310,6 @@ __device__ __forceinline__ void coop_vrr(const CoopArgs &p, double *B, int lane,
     }
 }
 
-__global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
-{
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *B = smem + (size_t)wib * p.buf;
-    const int64_t warp0 = (int64_t)blockIdx.x * COOP_WARPS + wib, nwarps = (int64_t)gridDim.x * COOP_WARPS;
-    for (int64_t q = warp0; q < p.ntasks; q += nwarps) {
-        const int2 t = p.tasks[q];
-        const double *gb = p.bra.geom + 8 * (int64_t)t.x, *gk = p.ket.geom + 8 * (int64_t)t.y;
-        const double A[3] = {gb[0], gb[1], gb[2]}, AB[3] = {gb[3], gb[4], gb[5]};
-        const double CD[3] = {gk[3], gk[4], gk[5]};
-        const int pb0 = p.bra.prim_off[t.x], pb1 = p.bra.prim_off[t.x + 1];
-        const int pk0 = p.ket.prim_off[t.y], pk1 = p.ket.prim_off[t.y + 1];
-        for (int i = lane; i < p.acc_n; i += 32) B[p.acc_off + i] = 0.0;
-        for (int pb = pb0; pb < pb1; ++pb) {
-            const double *rb = p.bra.prim + 8 * (int64_t)pb;
-            const double zeta = __ldg(rb), P[3] = {__ldg(rb + 1), __ldg(rb + 2), __ldg(rb + 3)};
-            const double Kab = __ldg(rb + 4), bx = __ldg(rb + 5), i2z = __ldg(rb + 6);
-            const double PA[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
-            for (int pk = pk0; pk < pk1; ++pk) {
-                const double *rk = p.ket.prim + 8 * (int64_t)pk;
-                const double eta = __ldg(rk), Q[3] = {__ldg(rk + 1), __ldg(rk + 2), __ldg(rk + 3)};
-                const double Kcd = __ldg(rk + 4), dx = __ldg(rk + 5), i2e = __ldg(rk + 6);
-                const double rs = rsqrt(zeta + eta), inv = rs * rs, rz = eta * inv;
-                const double PQ[3] = {P[0] - Q[0], P[1] - Q[1], P[2] - Q[2]};
-                const double T = zeta * rz * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
-                const double WP[3] = {-rz * PQ[0], -rz * PQ[1], -rz * PQ[2]};
-                const double ie = 2.0 * i2e, zoe = zeta * ie;
-                const double k0[3] = {-(bx * AB[0] + dx * CD[0]) * ie, -(bx * AB[1] + dx * CD[1]) * ie,
-                                      -(bx * AB[2] + dx * CD[2]) * ie};
-                double Fm[9];
-                boys_rt(p.boys, p.boys_inv, T, Kab * Kcd * rs, p.L, Fm);
-                __syncwarp();                              // previous accumulate has read S
-                if (lane <= p.L) B[lane] = Fm[lane];
-                __syncwarp();
-                // Entries of one level are independent, so each lane takes COOP_BATCH of them at a
-                // time: all op records first (global, L1/L2), then all sources (shared), then the
-                // arithmetic and the stores -- otherwise every entry pays the full load latency.
-                coop_vrr(p, B, lane, PA, WP, i2z, rz);
-                for (int lv = 0; lv < p.nxfer; ++lv) {
-                    const Op *ops = p.ops + p.xfer[lv].first;
-                    const int n = p.xfer[lv].count;
-                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
-                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH], sc[COOP_BATCH], sd[COOP_BATCH];
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) {
-                            sa[u] = B[o[u].a]; sb[u] = B[o[u].b];
-                            sc[u] = o[u].c >= 0 ? B[o[u].c] : 0.0; sd[u] = o[u].d >= 0 ? B[o[u].d] : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u)
-                            if (i0 + 32 * u < n)
-                                B[o[u].dst] = fma(o[u].n2 * i2e, sd[u], fma(o[u].n1 * i2e, sc[u], fma(k0[o[u].ax], sa[u], -zoe * sb[u])));
-                    }
-                    __syncwarp();
-                }
-                {
-                    const Op *ops = p.ops + p.acc.first;
-                    const int n = p.acc.count;
-                    for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
-                        Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH];
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u) { sa[u] = B[o[u].a]; sb[u] = B[o[u].dst]; }
-#pragma unroll
-                        for (int u = 0; u < COOP_BATCH; ++u)
-                            if (i0 + 32 * u < n) B[o[u].dst] = sb[u] + sa[u];
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        for (int lv = 0; lv < p.nhrr; ++lv) {
-            const Op *ops = p.ops + p.hrr[lv].first;
-            const int n = p.hrr[lv].count;
-            for (int i0 = lane; i0 < n; i0 += 32 * COOP_BATCH) {
-                Op o[COOP_BATCH]; double sa[COOP_BATCH], sb[COOP_BATCH];
-#pragma unroll
-                for (int u = 0; u < COOP_BATCH; ++u) o[u] = ld_op(ops, i0 + 32 * u, n);
-#pragma unroll
-                for (int u = 0; u < COOP_BATCH; ++u) { sa[u] = B[o[u].a]; sb[u] = o[u].ax >= 0 ? B[o[u].b] : 0.0; }
-#pragma unroll
-                for (int u = 0; u < COOP_BATCH; ++u)
-                    if (i0 + 32 * u < n) {
-                        const int ax = o[u].ax >= 0 ? o[u].ax : 0;
-                        B[o[u].dst] = fma(o[u].n2 ? CD[ax] : AB[ax], sb[u], sa[u]);
-                    }
-            }
-            __syncwarp();
-        }
-        const int2 sb = p.bra.shells[t.x], sk = p.ket.shells[t.y];
-        const double *sA = p.shell_scale + 6 * sb.x, *sB = p.shell_scale + 6 * sb.y;
-        const double *sC = p.shell_scale + 6 * sk.x, *sD = p.shell_scale + 6 * sk.y;
-        for (int c = lane; c < p.ncomp; c += 32) {
-            const int d = c % p.ND, cc = (c / p.ND) % p.NCc, b = (c / (p.ND * p.NCc)) % p.NB, a = c / (p.ND * p.NCc * p.NB);
-            p.out[(int64_t)c * p.ntasks + q] = B[p.y_off + c] * sA[a] * sB[b] * sC[cc] * sD[d];
-        }
-        __syncwarp();
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // Second-generation cooperative kernel (compiled per class): only the vertical recurrence is still
 // table-driven.  ncu on the interpreter above (profiles/r01): issue slots 61 % busy with the FP64
@@ -432,7 +327,6 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop_kernel(CoopArgs p)
 //     acc[cf] when g is in the contracted range (<= 32 stacked components for every d-rich class);
 //   * horizontal recurrences run on register rows with the thread kernels' hrr_apply: bra with one
 //     lane per stacked ket component, ket with one lane per (a,b) pair, transposed through shared memory.
-// QBX_COOP2=0 routes these classes back to the interpreter (A/B, and the reference for the tests).
 template <int LA, int LB, int LC, int LD>
 struct Coop2 {
     static constexpr int E = LA + LB, F = LC + LD, L = E + F;
@@ -715,28 +609,14 @@ int qbx_launch_eri_coop(int la, int lb, int lc, int ld, const ClassArgs &a, cuda
     for (int i = 0; i < c.nhrr; ++i) c.hrr[i] = P->hrr[i];
     c.acc = P->acc;
     for (int k = 0; k < QBX_BOYS_DEG; ++k) c.boys_inv[k] = 1.0 / (2.0 * (P->L + k) + 1.0);
-    static int use2 = getenv("QBX_COOP2") ? atoi(getenv("QBX_COOP2")) : 1;
-    if (use2) {
-        if (Coop2Launch f = coop2_for(la, lb, lc, ld)) {
-            const int rc2 = f(c, a.ntasks, s);
-            if (rc2 != -2) return rc2;
-            use2 = 0;                             // launch failure: stay on the first-generation kernel
-        }
+    // The table-driven first-generation kernel (an interpreter over the op table, 1.5-4.4x slower per class: 30.98 vs
+    // 28.63 ms for the (H2O)16 ERI pass, profiles/r02/probe_ab_head_of_round1.log) was deleted in round 2; its op table
+    // survives as the vertical-recurrence program of the compiled kernel.  A class the compiled kernel does not
+    // cover goes to its thread-per-quartet kernel (-1).
+    if (Coop2Launch f = coop2_for(la, lb, lc, ld)) {
+        const int rc2 = f(c, a.ntasks, s);
+        if (rc2 == -2) { qbx_set_error("eri_coop2_kernel could not be launched"); return QBX_ERR_CUDA; }
+        return rc2;
     }
-    const size_t smem = (size_t)COOP_WARPS * P->buf_doubles * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        QBX_CUDA(cudaFuncSetAttribute(eri_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    if (smem > 227 * 1024) { qbx_set_error("internal: cooperative ERI kernel buffer exceeds shared memory"); return QBX_ERR_STATE; }
-    int dev = 0, sms = 0, per_sm = 0;
-    QBX_CUDA(cudaGetDevice(&dev));
-    QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_coop_kernel, COOP_WARPS * 32, smem));
-    const int64_t need = (a.ntasks + COOP_WARPS - 1) / COOP_WARPS;
-    const int64_t cap = (int64_t)sms * std::max(per_sm, 1);
-    eri_coop_kernel<<<(unsigned)std::min(need, cap), COOP_WARPS * 32, smem, s>>>(c);
-    QBX_CUDA(cudaGetLastError());
-    return QBX_OK;
+    return -1;
 }

@@ -262,7 +262,7 @@ int launch_group(GroupArgs a, cudaStream_t s)
 }
 
 
-// ---- group-pair primitive records on the device (QBX_DEVICE_PAIRS=1, see engine.cu: k_pair_count / k_pair_fill)
+// ---- group-pair primitive records on the device (see engine.cu: k_pair_count / k_pair_fill)
 struct GroupTables {
     const double *gcen;          // [npg][3] centre of a primitive group
     const int *gxoff;            // [npg + 1] exponents of group g at gxpn[gxoff[g] ..]
@@ -389,8 +389,8 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
     for (auto &m : members)
         if (m.size() > QBX_GRP_MAXMEM) { qbx_set_error("internal: group pair with more than 9 members"); return QBX_ERR_STATE; }
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
-    if (d_ss_pairs && ng0 > 0) {
-        // ---- device path (QBX_DEVICE_PAIRS=1): count -> host sort by count -> fill
+    if (ng0 > 0) {
+        // ---- records on the device: count -> host sort by count -> fill
         cudaStream_t st = qbx_stream();
         std::vector<double> gcen(3 * pgs.size()), gxpn, scoef;
         std::vector<int> gxoff(pgs.size() + 1, 0), scoef_off(sh.size() + 1, 0), gmem(ng0 * QBX_GRP_MAXMEM, -1);
@@ -466,84 +466,8 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         qbx_pool_free_async(d_cnt); qbx_pool_free_async(d_order);
         return QBX_OK;
     }
-    // 3. primitive pairs of each group pair: geometry + the members' coefficient products
-    struct Rec { double v[QBX_GRP_NF]; };
-    std::vector<std::vector<Rec>> prims(ng0);
-    qbx_parallel_for(ng0, 32, [&](size_t lo, size_t hi) {
-    for (size_t g = lo; g < hi; ++g) {
-        const PG &P = pgs[gp_pq[g].first], &Q = pgs[gp_pq[g].second];
-        double pq2 = 0;
-        for (int d = 0; d < 3; ++d) pq2 += (P.cen[d] - Q.cen[d]) * (P.cen[d] - Q.cen[d]);
-        for (size_t a = 0; a < P.xpn.size(); ++a)
-            for (size_t b = 0; b < Q.xpn.size(); ++b) {
-                const double x = P.xpn[a], y = Q.xpn[b], z = x + y;
-                Rec r;
-                r.v[0] = z;
-                for (int d = 0; d < 3; ++d) r.v[1 + d] = (x * P.cen[d] + y * Q.cen[d]) / z;
-                r.v[4] = pref * exp(-x * y / z * pq2) / z;
-                double big = 0;
-                for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
-                    double cc = 0.0;
-                    if (m < (int)members[g].size()) {
-                        const int2 cd = ss_pairs[members[g][m]];
-                        // member (C,D): C may belong to P or to Q
-                        if (pg_of[cd.x] == gp_pq[g].first) cc = coef[cd.x][a] * coef[cd.y][b];
-                        else cc = coef[cd.y][a] * coef[cd.x][b];
-                    }
-                    r.v[5 + m] = cc;
-                    big = std::max(big, fabs(cc * r.v[4]));
-                }
-                if (big < 1e-24) continue;
-                if (prims[g].empty()) prims[g].reserve(P.xpn.size() * Q.xpn.size());
-                prims[g].push_back(r);
-            }
-    }
-    });
-    // 4. order groups by primitive count (descending, stable) and upload
-    std::vector<int> order(ng0);
-    for (size_t g = 0; g < ng0; ++g) order[g] = (int)g;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prims[x].size() > prims[y].size(); });
-    out.ng = (int)ng0;
-    out.h_nprim.resize(ng0); out.h_nmem.resize(ng0);
-    std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0);
-    for (size_t n = 0; n < ng0; ++n) {
-        const int g = order[n];
-        out.h_nprim[n] = (int)prims[g].size();
-        out.h_nmem[n] = (int)members[g].size();
-        for (size_t m = 0; m < members[g].size(); ++m) mem[n * QBX_GRP_MAXMEM + m] = members[g][m];
-        poff[n + 1] = poff[n] + (int)prims[g].size();
-    }
-    std::vector<double> soa((size_t)QBX_GRP_NF * poff.back());     // every element is written below
-    std::vector<int2> soa_idx(ng0);
-    size_t base = 0, g0 = 0;
-    while (g0 < ng0) {
-        size_t g1 = g0;
-        while (g1 < ng0 && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
-        const size_t gs = g1 - g0, np = (size_t)out.h_nprim[g0];
-        for (size_t n = g0; n < g1; ++n) soa_idx[n] = make_int2((int)(base + (n - g0)), (int)gs);
-        base += gs * np * QBX_GRP_NF;
-        g0 = g1;
-    }
-    qbx_parallel_for(ng0, 16, [&](size_t lo, size_t hi) {          // transposition: groups are independent
-        for (size_t n = lo; n < hi; ++n) {
-            const size_t b0 = (size_t)soa_idx[n].x, gs = (size_t)soa_idx[n].y, np = (size_t)out.h_nprim[n];
-            const Rec *r = prims[order[n]].data();
-            for (size_t pp = 0; pp < np; ++pp)
-                for (int k = 0; k < QBX_GRP_NF; ++k) soa[b0 + (pp * QBX_GRP_NF + k) * gs] = r[pp].v[k];
-        }
-    });
-    QBX_CUDA(qbx_dmalloc(&out.nmem, std::max<size_t>(1, ng0) * sizeof(int)));
-    QBX_CUDA(qbx_dmalloc(&out.members, std::max<size_t>(1, mem.size()) * sizeof(int)));
-    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
-    QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, soa.size()) * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, ng0) * sizeof(int2)));
-    if (ng0) {
-        QBX_CUDA(cudaMemcpy(out.nmem, out.h_nmem.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice));
-        QBX_CUDA(cudaMemcpy(out.members, mem.data(), mem.size() * sizeof(int), cudaMemcpyHostToDevice));
-        QBX_CUDA(cudaMemcpy(out.soa_idx, soa_idx.data(), ng0 * sizeof(int2), cudaMemcpyHostToDevice));
-    }
-    QBX_CUDA(cudaMemcpy(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if (!soa.empty()) QBX_CUDA(cudaMemcpy(out.soa, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    out.ng = 0;                                              // no (ss) pairs: nothing to share
+    (void)pref;
     return QBX_OK;
 }
 

@@ -310,8 +310,9 @@ def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=
     (initializeHartreeFock :178-210 -> qbx_one_body / qbx_eri_store; getGcore :305-319 ->
     qbx_fock_build).  ``mode``: "stored" | "direct" | "dense" (default: stored when the packed
     unique ERIs fit comfortably, else direct).  ``comm``: optional object with
-    ``rank``, ``size`` and ``allreduce(ndarray) -> ndarray`` (multi-GPU: one process per GPU,
-    partial G summed over ranks -- see parallel.py)."""
+    ``rank``, ``size`` and ``allreduce(ndarray) -> ndarray`` (multi-GPU: one process per GPU; with
+    parallel.LibComm the partial G matrices are summed inside qbx_fock_build by the library's own NCCL
+    all-reduce, with parallel.TorchComm by torch.distributed)."""
     from .integrals import DeviceBasis, DeviceERI, elecKinetics, nucAttractions, overlaps
 
     if not isinstance(nucInfo, NuclearCluster):
@@ -335,8 +336,8 @@ def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=
 
     def gcore(DJ, DKs):
         Gs = eri.getGcore(DJ, DKs)
-        if comm is not None and size > 1:
-            Gs = [comm.allreduce(G) for G in Gs]
+        if comm is not None and size > 1 and not getattr(comm, "in_library", False):
+            Gs = [comm.allreduce(G) for G in Gs]       # (parallel.LibComm: the library has already summed the shards)
         return Gs
 
     def sad():

@@ -36,6 +36,10 @@ SIGNATURES = {
     "qbx_prim_batch": [C.c_int] * 5 + [C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p],
     "qbx_stats": [C.c_void_p, C.c_void_p, C.c_int],
+    "qbx_comm_unique_id": [C.c_void_p],
+    "qbx_comm_init": [C.c_int, C.c_int, C.c_void_p],
+    "qbx_comm_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "qbx_comm_destroy": [],
 }
 
 

@@ -54,6 +54,54 @@ class TorchComm:
         self.dist.barrier()
 
 
+class LibComm:
+    """The communicator INSIDE the boundary (include/qbx.h: qbx_comm_init): every qbx_fock_build of a store that was
+    cut into ``size`` shards ends in one ncclAllReduce issued by libqbx.so itself, so the host code -- like the
+    reference's getG (HartreeFock.jl:322-327) -- receives the full G and has no reduction of its own.  The 128-byte
+    NCCL id travels from rank 0 to the others through ``exchange`` (default: a torch.distributed broadcast over
+    whatever process group exists; a Julia host would use MPI.jl / Distributed.jl -- INTEGRATION.md)."""
+    in_library = True
+
+    def __init__(self, rank=None, size=None, exchange=None):
+        import ctypes as C
+        from . import lib as L
+        if rank is None or size is None:
+            rank, size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank, self.size = rank, size
+        L.init()
+        uid = np.zeros(128, dtype=np.uint8)
+        if size > 1:
+            if rank == 0:
+                L.check(L.load().qbx_comm_unique_id(L.ptr(uid)))
+            uid = (exchange or self._torch_broadcast)(uid)
+        L.check(L.load().qbx_comm_init(rank, size, L.ptr(np.ascontiguousarray(uid)) if size > 1 else None))
+        r, n = C.c_int(-1), C.c_int(-1)
+        L.check(L.load().qbx_comm_info(C.byref(r), C.byref(n)))
+        assert (r.value, n.value) == (rank, size)
+
+    @staticmethod
+    def _torch_broadcast(uid):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("LibComm needs an initialised torch.distributed process group (or an `exchange` callable) "
+                               "to hand the NCCL id to the other ranks")
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(uid.copy()).to(dev)
+        dist.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    def allreduce(self, a):                # already summed inside qbx_fock_build
+        return a
+
+    def barrier(self):
+        pass
+
+    def close(self):
+        from . import lib as L
+        L.check(L.load().qbx_comm_destroy())
+
+
 class LocalComm:
     """Single-process stand-in (rank 0 of 1)."""
     rank, size = 0, 1

@@ -28,9 +28,10 @@ def test_header_symbols_are_exported(built):
     declared = set(re.findall(r"\b(qbx_[a-z0-9_]+)\s*\(", hdr))
     assert declared >= {"qbx_init", "qbx_basis_create", "qbx_eri_tensor", "qbx_eri_quartets", "qbx_eri_store",
                         "qbx_fock_build", "qbx_fock_build_device", "qbx_one_body", "qbx_boys", "qbx_prim_batch"}
+    # the WHOLE dynamic symbol table (functions and data, any binding), not just the qbx_* names
     nm = subprocess.check_output(["nm", "-D", "--defined-only", L.LIB_PATH], text=True)
-    exported = set(re.findall(r" T (qbx_[a-z0-9_]+)", nm))
-    assert declared == exported, (declared - exported, exported - declared)
+    exported = {ln.split()[-1] for ln in nm.splitlines() if ln.strip()}
+    assert declared == exported, (declared - exported, sorted(exported - declared)[:20])
     for name in declared:
         assert isinstance(getattr(built, name), ctypes._CFuncPtr)
     assert set(L.SIGNATURES) | {"qbx_last_error"} == declared
@@ -77,3 +78,16 @@ def test_nuclear_cluster_sorting():
     c = qb.NuclearCluster(["O", "H", "H"], [(0, 0, 0), (1, 0, 0), (-1, 0, 0)])
     assert c.syms == ["H", "H", "O"] and c.coords[0] == (-1.0, 0.0, 0.0)        # Particles.jl:29-55
     assert qb.nucRepulsion(c) == pytest.approx(8 + 8 + 0.5)
+
+
+def test_communicator_single_rank_needs_no_nccl(built):
+    """qbx_comm_init(0, 1, NULL) is legal without NCCL or a GPU; a multi-rank communicator needs the 128-byte id."""
+    r, n = ctypes.c_int(-1), ctypes.c_int(-1)
+    assert built.qbx_comm_destroy() == 0
+    assert built.qbx_comm_info(ctypes.byref(r), ctypes.byref(n)) == 0 and (r.value, n.value) == (0, 1)
+    assert built.qbx_comm_init(0, 1, None) == 0
+    assert built.qbx_comm_info(ctypes.byref(r), ctypes.byref(n)) == 0 and (r.value, n.value) == (0, 1)
+    assert built.qbx_comm_init(0, 2, None) == 1 and b"bad argument" in built.qbx_last_error()
+    assert built.qbx_comm_init(3, 2, None) == 1
+    assert built.qbx_comm_unique_id(None) == 1
+    assert built.qbx_comm_destroy() == 0

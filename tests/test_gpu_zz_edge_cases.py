@@ -95,6 +95,28 @@ def test_empty_quartet_list_and_zero_densities(backend):
     assert len(G) == 2 and not np.any(G[0]) and not np.any(G[1])
 
 
+def test_non_symmetric_density_is_rejected_not_silently_wrong(backend):
+    """The packed-store digestion is only valid for symmetric DJ / DK (include/qbx.h).  A non-symmetric argument used to
+    give a mode-dependent result (off by 6.8 in modes 0/1, exact in mode 2); now modes 0 and 1 refuse it
+    and mode 2 (dense tensor, the reference's formula term by term) still accepts it."""
+    from quiqbox_b200 import lib as L
+    db = qb.DeviceBasis(_MIX)
+    n = db.nbf
+    rng = np.random.RandomState(11)
+    DJ, DK = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    Tref = oracle.OracleBasis(db.data).eri_tensor(canonical=True)
+    Gd = qb.DeviceERI(db, mode="dense").getGcore(DJ, [DK])[0]
+    assert np.max(np.abs(Gd - oracle.getGcore(Tref, DJ, DK))) < 1e-10       # the reference's formula incl. its Hermitian fill
+    for mode in ("stored", "direct"):
+        eri = qb.DeviceERI(db, mode=mode, screen_tol=0.0)
+        with pytest.raises(L.QbxError, match="symmetric"):
+            eri.getGcore(DJ, [DK])
+        with pytest.raises(L.QbxError, match="symmetric"):
+            eri.getGcore((DJ + DJ.T) / 2, [DK])
+        Gs = eri.getGcore((DJ + DJ.T) / 2, [(DK + DK.T) / 2])[0]                 # and the symmetric parts are fine
+        assert np.max(np.abs(Gs - oracle.getGcore(Tref, (DJ + DJ.T) / 2, (DK + DK.T) / 2))) < 1e-10
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_small_bases(backend, seed):
     """Random shells (l <= 2, 1-4 primitives, 2-3 centres, some coincident; exponents 1e-2..1e4 for s, ..1e2 for p,
@@ -121,34 +143,43 @@ def test_random_small_bases(backend, seed):
         assert np.max(np.abs(G - Gref)) < 1e-9 * max(1.0, float(np.max(np.abs(Gref)))), (mode, tol)
 
 
+def _unique_quartets(n):
+    p = [(i, j) for j in range(n) for i in range(j + 1)]
+    return np.array([(p[a][0], p[a][1], p[b][0], p[b][1]) for a in range(len(p)) for b in range(a + 1)], dtype=np.int64)
+
+
 def test_tight_contracted_shells_keep_their_digits(backend):
     """Contracted shells with tight primitives (d exponent 285, p 663, s 5000: transition-metal-like) on two centres.
     The first cooperative kernel and the round-1 measurements used the electron transfer [e0|f0] -> [e0|f+1,0] for
     every class; at shell level it multiplies rounding by zeta/eta per level and lost 2e-7 of the largest element in
     (dd|dd) for this d contraction (found by test_random_small_bases with unrestricted exponent ranges).  The d-rich
-    classes now run a vertical recurrence on the ket (eri_coop2_kernel); the thread kernels keep the transfer, whose
-    <= 2 levels stay at rounding level here.  Bound: 1e-11 of the largest element of each class -- the oracle's own
-    8 permutational images of one integral differ by up to 8e-10 on this basis (orientation-dependent rounding of
-    the reference algorithm), so it cannot certify more."""
+    classes now run a vertical recurrence on the ket (eri_coop2_kernel).
+
+    Reference value: the QUAD-PRECISION arbiter (oracle/qbx_oracle_q.c), because on this basis the Float64 oracle's
+    own 8 permutational images of one integral differ by up to 8e-10.  Bound: 1e-11 of the largest element of each
+    class for every class, and the 1e-10 absolute bar of BASELINE.json on every unique entry."""
     c1, c2 = (-0.31, 1.92, 0.44), (1.27, -0.65, 2.03)
     bs = (shell(c1, [284.982, 2.254, 0.124], [0.55, -0.71, 0.32], 2) + shell(c2, [0.293], [1.0], 2) +
           shell(c1, [663.0, 18.4, 0.9], [0.1, 0.5, 0.6], 1) + shell(c2, [0.31], [1.0], 1) +
           shell(c1, [5000.0, 40.0, 1.1], [0.05, 0.4, 0.7], 0) + shell(c2, [0.2], [1.0], 0))
     db = qb.DeviceBasis(bs)
     ob = oracle.OracleBasis(db.data)
-    Tref = ob.eri_tensor(canonical=True)
     T = qb.elecRepulsions(db)
+    idx = _unique_quartets(db.nbf)
+    exact = oracle.eri_list_quad(ob, idx)
+    got = T[tuple(idx.T)]
     l = np.array([sum(b.ang) for b in bs])
-    L4 = l[np.indices(T.shape).reshape(4, -1)]
+    L4 = l[idx.T]
     key = np.sort(np.stack([np.maximum(L4[0], L4[1]) * 10 + np.minimum(L4[0], L4[1]),
                             np.maximum(L4[2], L4[3]) * 10 + np.minimum(L4[2], L4[3])]), axis=0)
     code = key[1] * 100 + key[0]
-    err, ref = np.abs(T - Tref).reshape(-1), np.abs(Tref).reshape(-1)
+    err, ref = np.abs(got - exact), np.abs(exact)
+    assert err.max() < 1e-10, float(err.max())
     for c in np.unique(code):
         m = code == c
-        bound = 1e-9 if c == 2121 else 1e-11          # (dp|dp): the oracle's own images differ by 8e-10 / 43 here
-        assert err[m].max() <= bound * ref[m].max(), (int(c), float(err[m].max()), float(ref[m].max()))
+        assert err[m].max() <= 1e-11 * ref[m].max(), (int(c), float(err[m].max()), float(ref[m].max()))
     dd = shell(c1, [284.982, 2.254, 0.124], [0.55, -0.71, 0.32], 2) + shell(c2, [0.293], [1.0], 2)
     d2 = qb.DeviceBasis(dd)
-    R2 = oracle.OracleBasis(d2.data).eri_tensor(canonical=True)
-    assert np.max(np.abs(qb.elecRepulsions(d2) - R2)) < 1e-12 * np.max(np.abs(R2))        # was 2e-7 with the transfer
+    i2 = _unique_quartets(d2.nbf)
+    R2 = oracle.eri_list_quad(oracle.OracleBasis(d2.data), i2)
+    assert np.max(np.abs(qb.elecRepulsions(d2)[tuple(i2.T)] - R2)) < 1e-12 * np.max(np.abs(R2))      # was 2e-7 with the transfer

@@ -30,7 +30,7 @@ CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
 if SAN:
     FLAGS = [f for f in FLAGS if f not in ("-O1", "-g0")] + ["-O1", "-g", "-fno-omit-frame-pointer", f"-fsanitize={SAN}"]
-UNITS = ["api", "generic", "engine", "eri_coop", "eri_group", "pool"]
+UNITS = ["api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm"]
 
 _launch = re.compile(r"([A-Za-z_]\w*(?:\s*<[^<>;(){}]*>)?)\s*<<<")
 
@@ -150,7 +150,7 @@ def build(jobs=None, force=False, verbose=False):
                 if rc != 0:
                     raise RuntimeError(f"{CXX} failed for {obj}:\n{out[-6000:]}")
     if work or not os.path.exists(LIB):
-        r = subprocess.run([CXX, "-shared", "-pthread", "-o", LIB] + ([f"-fsanitize={SAN}"] if SAN else []) + objs, capture_output=True, text=True)
+        r = subprocess.run([CXX, "-shared", "-pthread", "-o", LIB] + ([f"-fsanitize={SAN}"] if SAN else []) + objs + ["-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
         if verbose:

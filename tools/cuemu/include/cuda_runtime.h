@@ -127,6 +127,7 @@ static inline double max(double a, double b) { return fmax(a, b); }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 template <class T> static inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
@@ -183,6 +184,17 @@ static inline int __all_sync(unsigned m, int pred)
     return b == cuemu::active_mask(p);
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __reduce_min_sync(unsigned, int v)
+{
+    const int p = cuemu::xchg_parity();
+    *cuemu::xchg_slot(p, cuemu::cur->lane) = (uint64_t)(int64_t)v;
+    cuemu::warp_barrier();
+    const unsigned act = cuemu::active_mask(p);
+    int r = 0x7fffffff;
+    for (int l = 0; l < 32; ++l)
+        if ((act >> l) & 1u) { const int x = (int)(int64_t)*cuemu::xchg_slot(p, l); if (x < r) r = x; }
+    return r;
+}
 // lanes (among the live ones) that hold the same value as the caller
 template <class T> static inline unsigned __match_any_sync(unsigned, T v)
 {

@@ -16,6 +16,10 @@ template <class A> inline cuemu_policy par(A &) { return cuemu_policy(); }
 template <class T> using greater = std::greater<T>;
 template <class T> using less = std::less<T>;
 template <class P, class It> inline void sequence(const P &, It first, It last) { std::iota(first, last, 0); }
+template <class P, class It, class Out> inline Out inclusive_scan(const P &, It first, It last, Out out)
+{
+    return std::partial_sum(first, last, out);
+}
 template <class P, class K, class V, class Cmp>
 inline void stable_sort_by_key(const P &, K kfirst, K klast, V vfirst, Cmp cmp)
 {

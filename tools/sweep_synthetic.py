@@ -70,7 +70,7 @@ def main():
             L.check(lib.qbx_prim_batch(*cls, K, nq, 42, C.byref(secs), C.byref(chk), C.byref(npq), 0, None, None))
             tf = (npq.value * pf + nq * hf) / secs.value * 1e-12           # evaluated primitive quartets only
             cells.append(f"{tf:.2f} ({nq / secs.value * 1e-6:.1f}; {npq.value / (nq * K ** 4) * 100:.0f}%)")
-        kern = ("warp-coop2" if os.environ.get("QBX_COOP2", "1") != "0" else "warp-coop") if nacc >= 180 else "thread"
+        kern = "warp-coop2" if nacc >= 180 else "thread"
         print(f"| ({'spd'[cls[0]]}{'spd'[cls[1]]}\\|{'spd'[cls[2]]}{'spd'[cls[3]]}) | {kern} | " + " | ".join(cells) + " |", flush=True)
 
 
