@@ -174,6 +174,39 @@ QBX_API int qbx_pool_trim(int64_t *counts);
  * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */
 QBX_API int qbx_stats(qbx_basis *b, double *out, int reset);
 
+/* ---- the SCF step on the device.  getCDFE (src/HartreeFock.jl:392-403) -- solveFockMatrix
+ * through X = S^(-1/2) (:39-56; `eigen` via cuSOLVER), getD (:296-302), getG / getF (:322-335; the Fock build is
+ * qbx_fock_build_device incl. the all-reduce), getE (:339-350) -- plus the residual F D S - S D F (:1298) and the Gram
+ * matrices the DIIS family is built from (:1273-1316), with every N x N matrix resident in HBM; the host keeps the
+ * m x m coefficient problem and the stage logic.  S, Hcore: nbf^2 column-major (host); `history` = number of
+ * (D, F, residual) slots kept on the device.  A store must exist on the basis (qbx_eri_store). */
+typedef struct qbx_scf qbx_scf;
+QBX_API int qbx_scf_create(qbx_basis *b, const double *S, const double *Hcore, int history, qbx_scf **out);
+QBX_API int qbx_scf_destroy(qbx_scf *s);
+/* which: 0 = the matrix the next step diagonalises (F_in), 1 = coefficient matrix C; nbf^2 doubles, host */
+QBX_API int qbx_scf_set(qbx_scf *s, int which, int spin, const double *M);
+/* which: 0 F_in, 1 C, 2 D, 3 F, 4 orbital energies (nbf doubles), 5 X, 6 = four doubles: device seconds since creation in
+ * {eigen + transforms + density (a :DD step: incl. its first Fock build), the Fock builds, whole steps} and the step count */
+QBX_API int qbx_scf_get(qbx_scf *s, int which, int spin, double *M);
+/* One step for nspin sectors with nocc[spin] occupied orbitals.  from_coeff = 1 keeps the coefficients set with
+ * qbx_scf_set instead of diagonalising F_in; damp > 0 is the damped step :DD (:1245-1270; two Fock builds).
+ * out[0..1] = E per spin sector (getE), out[2] = mean over the sectors of RMS(F D S - S D F) (getErrorNrms, :1230),
+ * out[3] = RMS change of the total density. */
+QBX_API int qbx_scf_step(qbx_scf *s, int nspin, const int *nocc, int from_coeff, double damp, double *out);
+QBX_API int qbx_scf_hist_store(qbx_scf *s, int slot);
+/* Gdf[i][j] = <D_i, F_j>, Gee[i][j] = <e_i, e_j>, e = X^T (F D S - S D F) X over the m given slots (row-major m x m, host) */
+QBX_API int qbx_scf_hist_gram(qbx_scf *s, int spin, int m, const int *slots, double *Gdf, double *Gee);
+/* F_in[spin] = sum_i coef[i] F[slots[i]] */
+QBX_API int qbx_scf_combine(qbx_scf *s, int spin, int m, const int *slots, const double *coef);
+
+/* ---- changeOrbitalBasis (src/Integration/Interface.jl:376-407).
+ * out[i,j,k,l] = sum (ab|cd) C[a,i] C[b,j] C[c,k] C[d,l], C: nbf x nmo column-major, out: nmo^4 doubles column-major
+ * (host); four quarter transforms as FP64 GEMMs over the dense tensor on the device (the mode-2 store if present,
+ * else built for the call: nbf^4 * 8 bytes must fit).  qbx_mo_coulomb_ab is the third element of the two-coefficient
+ * method: J[m,n] = sum (ab|cd) C1[a,m] C1[b,m] C2[c,n] C2[d,n], nmo1 x nmo2 column-major. */
+QBX_API int qbx_mo_transform(qbx_basis *b, int64_t nmo, const double *C, double *out, int64_t out_bytes);
+QBX_API int qbx_mo_coulomb_ab(qbx_basis *b, int64_t nmo1, const double *C1, int64_t nmo2, const double *C2, double *out);
+
 #ifdef __cplusplus
 }
 #endif

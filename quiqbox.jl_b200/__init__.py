@@ -4,5 +4,5 @@ from .basis import (GTO, MultiOrbitalData, NuclearCluster, SubshellXYZs, genGaus
 from .hartreefock import (HFconfig, HFfinalInfo, RCHartreeFock, SCFconfig, UOHartreeFock,
                           runHartreeFockCore)
 from .hartreefock import runHartreeFock
-from .integrals import (DeviceBasis, DeviceERI, boys, coreHamiltonian, elecKinetics, elecRepulsion,
+from .integrals import (DeviceBasis, DeviceERI, DeviceSCF, boys, changeOrbitalBasis, coreHamiltonian, elecKinetics, elecRepulsion,
                         elecRepulsionList, elecRepulsions, getGcore, nucAttractions, overlaps)

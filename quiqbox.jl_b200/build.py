@@ -23,7 +23,7 @@ FLAGS += os.environ.get("QBX_NVCC_DEFS", "").split()
 
 CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
-HEADERS = ["boys.cuh", "qbx_internal.h", "eri_class.cuh", "digest.cuh", "engine.h", "../../include/qbx.h"]
+HEADERS = ["boys.cuh", "qbx_internal.h", "eri_class.cuh", "digest.cuh", "engine.h", "handle.h", "linalg.h", "../../include/qbx.h"]
 
 
 def _newer(target, deps):
@@ -49,7 +49,7 @@ def build(jobs=None, force=False, verbose=True):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     work, objs = [], []
-    for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm"):
+    for name in ("api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm", "linalg", "scf"):
         src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):

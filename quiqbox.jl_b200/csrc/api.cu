@@ -94,7 +94,7 @@ extern "C" int qbx_shutdown(void)
     return QBX_OK;
 }
 
-static int ensure_init()
+int qbx_ensure_init()
 {
     if (g_device < 0) {
         int rc = qbx_init(0, nullptr);
@@ -104,28 +104,7 @@ static int ensure_init()
     return QBX_OK;
 }
 
-// ------------------------------------------------------------------ handle
-struct qbx_basis {
-    std::mutex mu;
-    // host copy of the boundary arrays
-    int64_t nprim = 0, nbf = 0;
-    std::vector<double> cen, xpn, bf_w;
-    std::vector<int32_t> ang;
-    std::vector<int64_t> bf_off, bf_prim;
-    DevFlat flat{};                     // device copy (generic kernels)
-    std::unique_ptr<Engine> eng;        // shell/class machinery (null if the basis is irregular)
-    int mode = -1;                      // qbx_eri_store mode, -1 = nothing stored
-    double *d_dense = nullptr;          // mode 2
-    double *d_DJ = nullptr, *d_DK = nullptr, *d_G = nullptr;   // staging for host-pointer Fock builds
-    int staged_nmat = 0;
-    int nranks = 1;                     // shards the stored representation was cut into (qbx_eri_store)
-    double stats[16] = {0};
-};
-
-// comm.cu
-int qbx_comm_rank();
-int qbx_comm_size();
-int qbx_comm_allreduce(double *d_buf, size_t count, cudaStream_t s);
+#include "handle.h"
 
 template <class T>
 static int to_device(T **dst, const std::vector<T> &src)
@@ -142,7 +121,7 @@ extern "C" int qbx_basis_create(int64_t nprim, const double *cen, const double *
         qbx_set_error("qbx_basis_create: null or empty argument");
         return QBX_ERR_ARG;
     }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     const int64_t nnz = bf_off[nbf];
     if (bf_off[0] != 0 || nnz <= 0) { qbx_set_error("qbx_basis_create: bf_off must start at 0 and be non-empty"); return QBX_ERR_ARG; }
@@ -209,7 +188,7 @@ extern "C" int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, do
     if (n == 0) return QBX_OK;
     for (int64_t t = 0; t < 4 * n; ++t)
         if (ijkl[t] < 0 || ijkl[t] >= b->nbf) { qbx_set_error("qbx_eri_quartets: function index out of range"); return QBX_ERR_RANGE; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     int64_t *d_idx = nullptr; double *d_out = nullptr;
@@ -234,7 +213,7 @@ extern "C" int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes)
     if (!b || !out) { qbx_set_error("qbx_eri_tensor: null argument"); return QBX_ERR_ARG; }
     const int64_t N = b->nbf, need = N * N * N * N * (int64_t)sizeof(double);
     if (out_bytes < need) { qbx_set_error("qbx_eri_tensor: output buffer smaller than nbf^4 * 8 bytes"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     double *d_t = nullptr;
@@ -255,7 +234,7 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
         qbx_set_error("qbx_eri_store: bad argument");
         return QBX_ERR_ARG;
     }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     if (nranks > 1 && qbx_comm_size() == nranks && qbx_comm_rank() != rank) {
         qbx_set_error("qbx_eri_store: rank differs from the rank of this process in the communicator (qbx_comm_init)");
@@ -284,7 +263,7 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
 extern "C" int qbx_eri_recompute_async(qbx_basis *b)
 {
     if (!b) { qbx_set_error("qbx_eri_recompute: null handle"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     if (b->mode != 0 || !b->eng) { qbx_set_error("qbx_eri_recompute: call qbx_eri_store(mode = 0) first"); return QBX_ERR_STATE; }
@@ -301,7 +280,7 @@ extern "C" int qbx_eri_recompute(qbx_basis *b)
 
 extern "C" int qbx_set_stream(void *stream)
 {
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_mu);
     QBX_CUDA(cudaStreamSynchronize(g_stream));
@@ -312,7 +291,7 @@ extern "C" int qbx_set_stream(void *stream)
 extern "C" int qbx_class_stats(qbx_basis *b, double *out)
 {
     if (!b || !out) { qbx_set_error("qbx_class_stats: null argument"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     if (!b->eng) { qbx_set_error("qbx_class_stats: basis has no shell-class path"); return QBX_ERR_STATE; }
@@ -333,7 +312,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 extern "C" int qbx_fp64_peak(double *tflops)
 {
     if (!tflops) { qbx_set_error("qbx_fp64_peak: null argument"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     cudaDeviceProp prop;
     QBX_CUDA(cudaGetDeviceProperties(&prop, g_device));
@@ -359,7 +338,7 @@ extern "C" int qbx_fp64_peak(double *tflops)
     return QBX_OK;
 }
 
-static int fock_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s)
+int qbx_fock_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s)
 {
     if (b->mode < 0) { qbx_set_error("qbx_fock_build: call qbx_eri_store first"); return QBX_ERR_STATE; }
     if (b->mode == 2) {
@@ -376,16 +355,16 @@ static int fock_device(qbx_basis *b, int nmat, const double *dDJ, const double *
 extern "C" int qbx_fock_build_device(qbx_basis *b, int nmat, const double *dDJ, const double *dDK, double *dG, void *stream)
 {
     if (!b || nmat < 1 || nmat > 2 || !dDJ || !dDK || !dG) { qbx_set_error("qbx_fock_build_device: bad argument"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
-    return fock_device(b, nmat, dDJ, dDK, dG, stream ? (cudaStream_t)stream : g_stream);
+    return qbx_fock_device(b, nmat, dDJ, dDK, dG, stream ? (cudaStream_t)stream : g_stream);
 }
 
 extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const double *DK, double *G)
 {
     if (!b || nmat < 1 || nmat > 2 || !DJ || !DK || !G) { qbx_set_error("qbx_fock_build: bad argument (nmat must be 1 or 2)"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
@@ -415,7 +394,7 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
     }
     QBX_CUDA(cudaMemcpyAsync(b->d_DJ, DJ, n2, cudaMemcpyHostToDevice, g_stream));
     QBX_CUDA(cudaMemcpyAsync(b->d_DK, DK, n2 * nmat, cudaMemcpyHostToDevice, g_stream));
-    rc = fock_device(b, nmat, b->d_DJ, b->d_DK, b->d_G, g_stream);
+    rc = qbx_fock_device(b, nmat, b->d_DJ, b->d_DK, b->d_G, g_stream);
     if (rc) return rc;
     QBX_CUDA(cudaMemcpyAsync(G, b->d_G, n2 * nmat, cudaMemcpyDeviceToHost, g_stream));
     QBX_CUDA(cudaStreamSynchronize(g_stream));
@@ -428,7 +407,7 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
         qbx_set_error("qbx_one_body: bad argument");
         return QBX_ERR_ARG;
     }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
@@ -459,7 +438,7 @@ extern "C" int qbx_boys(int64_t n, const double *T, int mmax, int table, double 
     if (n == 0) return QBX_OK;
     for (int64_t i = 0; i < n; ++i)
         if (!(T[i] >= 0.0)) { qbx_set_error("qbx_boys: T must be >= 0"); return QBX_ERR_ARG; }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     double *dT = nullptr, *dO = nullptr;
     QBX_CUDA(qbx_dmalloc(&dT, n * sizeof(double)));
@@ -483,7 +462,7 @@ extern "C" int qbx_prim_batch(int la, int lb, int lc, int ld, int K, int64_t nqu
         qbx_set_error("qbx_prim_batch: bad argument (need la >= lb, lc >= ld, l <= 2, 1 <= K <= 16)");
         return QBX_ERR_ARG;
     }
-    int rc = ensure_init();
+    int rc = qbx_ensure_init();
     if (rc) return rc;
     return Engine::synthetic(la, lb, lc, ld, K, nquartets, seed, secs, checksum, prim_quartets, nsample, sample_out, sample_geom,
                              g_stream);

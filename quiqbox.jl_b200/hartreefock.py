@@ -218,6 +218,110 @@ def _xdiis_coeff(method, Ds, Fs, Es, S, X):
     return _simplex_min(v, B)
 
 
+def _xdiis_coeff_gram(method, Gdf, Gee, Es):
+    """The same coefficient problems as _xdiis_coeff, from the Gram matrices Gdf[i,j] = <D_i, F_j> and
+    Gee[i,j] = <e_i, e_j> (e = X^T (F D S - S D F) X) that the device SCF step returns (qbx_scf_hist_gram):
+    <D_i - D_j, F_i - F_j> = G_ii - G_ij - G_ji + G_jj etc."""
+    m = len(Es)
+    if method == "DIIS":
+        B = -np.ones((m + 1, m + 1)); B[m, m] = 0.0
+        B[:m, :m] = Gee
+        rhs = np.zeros(m + 1); rhs[m] = -1.0
+        try:
+            return np.linalg.solve(B, rhs)[:m]
+        except np.linalg.LinAlgError:
+            c = np.zeros(m); c[-1] = 1.0
+            return c
+    d = np.diag(Gdf)
+    if method == "EDIIS":
+        v = np.array(Es)
+        B = -(d[:, None] - Gdf - Gdf.T + d[None, :])
+    else:                                                    # ADIIS
+        n = m - 1
+        v = Gdf[:, n] - Gdf[n, n]
+        B = Gdf - Gdf[:, n][:, None] - Gdf[n, :][None, :] + Gdf[n, n]
+    return _simplex_min(v, B)
+
+
+def runHartreeFockCoreDevice(scf, Ns: Sequence[int], config: HFconfig, Cs0, printInfo=False):
+    """runHartreeFockCore with the SCF step on the device (integrals.DeviceSCF): same stages, same
+    history rules, same convergence test; per step the host receives the energies, two RMS norms and the m x m Gram
+    matrices of the extrapolation, nothing of size N^2.  ``Cs0``: initial coefficient matrices (the guess)."""
+    nspin = len(Ns)
+    nbuild = [0]
+    for s_, C0 in enumerate(Cs0):
+        scf.set("C", s_, C0)
+    Es, _, _ = scf.step(Ns, from_coeff=True)
+    nbuild[0] += 1
+    Etot = get2SpinQuantity(Es)
+    trace = [Etot]
+    free = list(range(scf.cap))
+    slot0 = free.pop(0)
+    scf.store(slot0)
+    hist = [dict(slot=[slot0], E=[Es[s_]]) for s_ in range(nspin)]          # per spin sector, as HFtempInfo keeps it
+
+    def release():
+        used = set(x for h in hist for x in h["slot"])
+        for k in range(scf.cap):
+            if k not in used and k not in free:
+                free.append(k)
+
+    ratioD, ratioF = config.strategy.secondaryConvRatio
+    step, converged = 0, False
+    stages = config.strategy.stages()
+    resetThreshold = 1000 * 4e-16
+    for si, (method, thr) in enumerate(stages):
+        stage_done = False
+        for h in hist:
+            for k in ("slot", "E"):
+                h[k] = h[k][-defaultDIISsize:]
+        release()
+        while step < config.maxStep:
+            step += 1
+            if method == "DD":
+                En, dF, dD = scf.step(Ns, damp=defaultDS)
+                nbuild[0] += 2
+            else:
+                for s_, h in enumerate(hist):
+                    if len(h["slot"]) > 1:
+                        Gdf, Gee = scf.gram(s_, h["slot"])
+                        c = _xdiis_coeff_gram(method, Gdf, Gee, h["E"])
+                    else:
+                        c = np.ones(1)
+                    scf.combine(s_, h["slot"], c)
+                En, dF, dD = scf.step(Ns)
+                nbuild[0] += 1
+            new = free.pop(0)
+            scf.store(new)
+            for s_, h in enumerate(hist):
+                h["slot"].append(new); h["E"].append(En[s_])
+                if method != "DD" and len(h["E"]) > 2 and h["E"][-1] - h["E"][-2] > resetThreshold:
+                    for k in ("slot", "E"):
+                        h[k] = h[k][-2:-1]
+                elif len(h["E"]) > defaultDIISsize:
+                    drop = int(np.argmax(h["E"]))
+                    for k in ("slot", "E"):
+                        h[k].pop(drop)
+            release()
+            Enew = get2SpinQuantity(En)
+            dE = Enew - Etot
+            Etot = Enew
+            trace.append(Etot)
+            if printInfo:
+                print(f"| {step:4d} | {method:5s} | {Etot: .12f} | {dE: .3e} | {dF:.3e} | {dD:.3e}")
+            if abs(dE) <= thr and dD <= ratioD * thr and dF <= ratioF * thr:
+                stage_done = True
+                break
+        if not stage_done:
+            break
+        converged = (si == len(stages) - 1)
+    Cs = tuple(scf.get("C", s_) for s_ in range(nspin))
+    Ds = tuple(scf.get("D", s_) for s_ in range(nspin))
+    Fs = tuple(scf.get("F", s_) for s_ in range(nspin))
+    eps = [scf.get("eps", s_) for s_ in range(nspin)]
+    return Cs, Ds, Fs, eps, Etot, converged, step, nbuild[0], trace
+
+
 def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFconfig,
                        sad: Optional[Callable] = None, printInfo=False):
     """HartreeFock.jl:1049-1228 on top of an abstract ``gcore`` (the hot-path call).
@@ -286,8 +390,8 @@ def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFc
             w = 2.0 if nspin == 1 else 1.0
             dD = float(np.sqrt(np.mean((w * sum(Dn2) - w * sum(Ds)) ** 2)))
             Cs, Ds, Fs, Etot = Cn, Dn2, Fn, Enew
-            dF = float(np.sqrt(np.mean(np.concatenate(
-                [(X.T @ (F @ D @ S - S @ D @ F) @ X).ravel() for F, D in zip(Fs, Ds)]) ** 2)))
+            # getErrorNrms (HartreeFock.jl:1230-1237): mean over the spin sectors of RMS(F D S - S D F)
+            dF = float(np.mean([np.sqrt(np.mean((F @ D @ S - S @ D @ F) ** 2)) for F, D in zip(Fs, Ds)]))
             trace.append(Etot)
             if printInfo:
                 print(f"| {step:4d} | {method:5s} | {Etot: .12f} | {dE: .3e} | {dF:.3e} | {dD:.3e}")
@@ -302,7 +406,7 @@ def runHartreeFockCore(S, Hcore, gcore: Callable, Ns: Sequence[int], config: HFc
 
 # ---------------------------------------------------------------------------- public entry
 def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=False, mode=None,
-                   screen_tol=1e-12, comm=None):
+                   screen_tol=1e-12, comm=None, device_scf=False, timings=None):
     """runHartreeFock(nucInfo, bs[, config]) -> HFfinalInfo  (HartreeFock.jl:953-1046).
 
     ``nucInfo`` is a NuclearCluster (or ``(nucSyms, nucCoords)``), ``bs`` a list of GTOs.  The
@@ -355,6 +459,26 @@ def runHartreeFock(nucInfo, bs, config: Optional[HFconfig] = None, *, printInfo=
             Da += out[1][0]; Db += out[1][1]
         return Da / len(nucInfo), Db / len(nucInfo)
 
-    Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCore(S, Hcore, gcore, Ns, config, sad, printInfo)
+    import time as _time
+    t_setup = _time.perf_counter()
+    if device_scf:
+        from .integrals import DeviceSCF
+        if comm is not None and size > 1 and not getattr(comm, "in_library", False):
+            raise ValueError("device_scf with several ranks needs parallel.LibComm (the all-reduce inside qbx_fock_build)")
+        nspin = len(Ns)
+        X = getOrthonormalization(S)
+        Cs0 = _guess(config.initial, nspin, X, S, Hcore, gcore, Ns, sad)
+        t_guess = _time.perf_counter()
+        scf = DeviceSCF(eri, S, Hcore)
+        Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCoreDevice(scf, Ns, config, Cs0, printInfo)
+        if timings is not None:
+            tm = scf.get("times")
+            timings.update(device_eigen_seconds=float(tm[0]), device_fock_seconds=float(tm[1]), device_step_seconds=float(tm[2]),
+                           device_steps=int(tm[3]), guess_seconds=t_guess - t_setup, scf_loop_seconds=_time.perf_counter() - t_guess)
+        scf.close()
+    else:
+        Cs, Ds, Fs, eps, E, conv, steps, nb, trace = runHartreeFockCore(S, Hcore, gcore, Ns, config, sad, printInfo)
+        if timings is not None:
+            timings.update(scf_loop_seconds=_time.perf_counter() - t_setup)
     return HFfinalInfo((E, nucRepulsion(nucInfo)), Cs, Ds, Fs, tuple(eps), conv, steps, nb,
                        trace if config.saveTrace else trace[-1:])

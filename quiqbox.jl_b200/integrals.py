@@ -153,6 +153,89 @@ class DeviceERI:
         return [G[m].reshape((n, n), order="F") for m in range(nmat)]
 
 
+def changeOrbitalBasis(eri, C, C2=None):
+    """changeOrbitalBasis(twoBodyInt, C[, C2]) (src/Integration/Interface.jl:376-407) with the two-electron integrals on
+    the device: ``out[i,j,k,l] = sum (ab|cd) C[a,i] C[b,j] C[c,k] C[d,l]`` (four FP64 GEMM quarter transforms,
+    qbx_mo_transform).  With two coefficient matrices (the unrestricted case) returns the reference's 3-tuple: the
+    transform for each, and the alpha-beta Coulomb matrix J[m,n] = (m m|n n) (qbx_mo_coulomb_ab).
+    ``eri``: a DeviceERI, a DeviceBasis or a list of GTOs.  A 2-D first argument is the one-body method (host)."""
+    if isinstance(eri, np.ndarray) and eri.ndim == 2:
+        return C.T @ eri @ C
+    b = eri.basis if isinstance(eri, DeviceERI) else _as_basis(eri)
+
+    def one(Cm):
+        Cm = np.asfortranarray(Cm, dtype=np.float64)
+        if Cm.shape[0] != b.nbf:
+            raise ValueError("DimensionMismatch: coefficient matrix does not match the basis.")
+        m = Cm.shape[1]
+        out = np.empty(m ** 4, dtype=np.float64)
+        _l.check(_l.load().qbx_mo_transform(b.handle, m, _l.ptr(Cm), _l.ptr(out), out.nbytes))
+        return out.reshape((m, m, m, m), order="F")
+
+    if C2 is None:
+        return one(C)
+    C1f, C2f = np.asfortranarray(C, dtype=np.float64), np.asfortranarray(C2, dtype=np.float64)
+    J = np.empty(C1f.shape[1] * C2f.shape[1], dtype=np.float64)
+    _l.check(_l.load().qbx_mo_coulomb_ab(b.handle, C1f.shape[1], _l.ptr(C1f), C2f.shape[1], _l.ptr(C2f), _l.ptr(J)))
+    return one(C1f), one(C2f), J.reshape((C1f.shape[1], C2f.shape[1]), order="F")
+
+
+class DeviceSCF:
+    """The SCF step on the device (include/qbx.h: qbx_scf_*; getCDFE, HartreeFock.jl:392-403): every N x N matrix --
+    S, Hcore, X, C, D, F, the (D, F, residual) history of the DIIS family -- stays in HBM, the host sees scalars and
+    the m x m Gram matrices.  ``eri`` must hold a store (DeviceERI)."""
+
+    def __init__(self, eri: DeviceERI, S, Hcore, history=24):
+        self.eri, self.n, self.cap = eri, eri.basis.nbf, history
+        h = C.c_void_p()
+        Sf, Hf = np.asfortranarray(S, dtype=np.float64), np.asfortranarray(Hcore, dtype=np.float64)
+        _l.check(_l.load().qbx_scf_create(eri.basis.handle, _l.ptr(Sf), _l.ptr(Hf), history, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _l.load().qbx_scf_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, which, spin, M):
+        Mf = np.asfortranarray(M, dtype=np.float64)
+        _l.check(_l.load().qbx_scf_set(self.handle, {"Fin": 0, "C": 1}[which], spin, _l.ptr(Mf)))
+
+    def get(self, which, spin=0):
+        code = {"Fin": 0, "C": 1, "D": 2, "F": 3, "eps": 4, "X": 5, "times": 6}[which]
+        out = np.empty(4 if code == 6 else (self.n if code == 4 else self.n * self.n))
+        _l.check(_l.load().qbx_scf_get(self.handle, code, spin, _l.ptr(out)))
+        return out if code in (4, 6) else out.reshape((self.n, self.n), order="F")
+
+    def step(self, nocc, from_coeff=False, damp=0.0):
+        """-> (E per spin sector, RMS(F D S - S D F) averaged over the sectors, RMS change of the total density)"""
+        no = np.ascontiguousarray(nocc, dtype=np.int32)
+        out = np.zeros(4)
+        _l.check(_l.load().qbx_scf_step(self.handle, len(no), _l.ptr(no), int(from_coeff), float(damp), _l.ptr(out)))
+        return tuple(out[:len(no)]), float(out[2]), float(out[3])
+
+    def store(self, slot):
+        _l.check(_l.load().qbx_scf_hist_store(self.handle, int(slot)))
+
+    def gram(self, spin, slots):
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        m = len(sl)
+        Gdf, Gee = np.zeros((m, m)), np.zeros((m, m))
+        _l.check(_l.load().qbx_scf_hist_gram(self.handle, spin, m, _l.ptr(sl), _l.ptr(Gdf), _l.ptr(Gee)))
+        return Gdf, Gee
+
+    def combine(self, spin, slots, coef):
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        cf = np.ascontiguousarray(coef, dtype=np.float64)
+        _l.check(_l.load().qbx_scf_combine(self.handle, spin, len(sl), _l.ptr(sl), _l.ptr(cf)))
+
+
 def getGcore(HeeI: DeviceERI, DJ, DK):
     """Drop-in for Quiqbox.getGcore (HartreeFock.jl:305-319) on a DeviceERI."""
     return HeeI.getGcore(DJ, [DK])[0]

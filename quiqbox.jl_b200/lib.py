@@ -40,6 +40,16 @@ SIGNATURES = {
     "qbx_comm_init": [C.c_int, C.c_int, C.c_void_p],
     "qbx_comm_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "qbx_comm_destroy": [],
+    "qbx_scf_create": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)],
+    "qbx_scf_destroy": [C.c_void_p],
+    "qbx_scf_set": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "qbx_scf_get": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "qbx_scf_step": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p],
+    "qbx_scf_hist_store": [C.c_void_p, C.c_int],
+    "qbx_scf_hist_gram": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    "qbx_scf_combine": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    "qbx_mo_transform": [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64],
+    "qbx_mo_coulomb_ab": [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
 }
 
 

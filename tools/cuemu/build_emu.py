@@ -30,7 +30,7 @@ CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3
            if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
 if SAN:
     FLAGS = [f for f in FLAGS if f not in ("-O1", "-g0")] + ["-O1", "-g", "-fno-omit-frame-pointer", f"-fsanitize={SAN}"]
-UNITS = ["api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm"]
+UNITS = ["api", "generic", "engine", "eri_coop", "eri_group", "pool", "comm", "linalg", "scf"]
 
 _launch = re.compile(r"([A-Za-z_]\w*(?:\s*<[^<>;(){}]*>)?)\s*<<<")
 
