@@ -223,8 +223,12 @@ def test_synthetic_class_batch_vs_oracle(cls):
     from quiqbox_b200 import lib as L
     la, lb, lc, ld = cls
     L.init()
-    for K in (1, 3):
-        nq, ns = 4096, (12 if np.prod([(l + 1) * (l + 2) // 2 for l in cls]) < 600 else 5)
+    nc_all = int(np.prod([(l + 1) * (l + 2) // 2 for l in cls]))
+    # contraction degrees of the sweep (BASELINE.json configs[4]: 1-6, plus the cc-pVDZ value 9): all of them where the
+    # quad-precision reference is affordable, K in {1, 3} for the classes with hundreds of components
+    Ks = (1, 2, 3, 4, 6, 9) if nc_all <= 3 else ((1, 2, 3, 4, 6) if nc_all <= 27 else (1, 3))
+    for K in Ks:
+        nq, ns = 4096, (12 if nc_all < 600 and K <= 4 else 5)
         ncomp = np.prod([(l + 1) * (l + 2) // 2 for l in cls])
         secs, chk, npq = C.c_double(), C.c_double(), C.c_double()
         out = np.zeros((ns, ncomp)); geom = np.zeros((ns, 4, 3 + 2 * K))

@@ -43,35 +43,49 @@ def model(la, lb, lc, ld):
     return 84 + 25 + 3 * Lt + vrr + acc, hrr
 
 
-def main():
+CLASSES = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
+           if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
+KS = [1, 2, 3, 4, 6, 9]
+
+
+def sweep(Ks=KS, classes=CLASSES):
+    """-> (measured FP64 peak in TFLOP/s, rows): one row per (class, K) with the device seconds of the ERI kernel, the
+    contracted quartets, the primitive quartets actually evaluated and the SURVEY.md 8(d) model flops."""
     L.init()
     lib = L.load()
     peak = C.c_double()
     L.check(lib.qbx_fp64_peak(C.byref(peak)))
-    classes = [(a, b, c, d) for a in range(3) for b in range(a + 1) for c in range(3) for d in range(c + 1)
-               if (a * (a + 1) // 2 + b) >= (c * (c + 1) // 2 + d)]
-    Ks = [1, 2, 3, 4, 6, 9]
-    print(f"# Synthetic shell-quartet sweep on one B200 (measured FP64 FMA peak {peak.value:.1f} TFLOP/s)\n")
-    print("Centres uniform in a 10-bohr cube, exponents log-uniform in [0.1, 1e3], coefficients in [-1, 1] (qbx_prim_batch, seed 42).")
-    print("Cells: model TFLOP/s (SURVEY.md 8d flop count over the primitive quartets actually EVALUATED / CUDA-event time of the ERI kernel); in brackets million contracted quartets per second and the share of the K^4 primitive quartets that survive the |K_ab| < 1e-24 primitive-pair cut-off (tight, distant pairs underflow).")
-    print("The 8d model counts a vertical recurrence on both centres; the kernels use the cheaper electron-transfer route, so a model rate can exceed the FP64 pipe's executed rate.\n")
-    print("| class | kernel | " + " | ".join(f"K={k}" for k in Ks) + " |")
-    print("|---|---|" + "---|" * len(Ks))
+    rows = []
     for cls in classes:
         ncomp = int(np.prod([nc(l) for l in cls]))
         pf, hf = model(*cls)
         nacc = sum(nc(e) for e in range(cls[0], cls[0] + cls[1] + 1)) * sum(nc(f) for f in range(cls[2], cls[2] + cls[3] + 1))
-        cells = []
         for K in Ks:
             nq = 1 << 20
             while nq * ncomp * 8 > 6e9 or nq * K ** 4 * pf > 4e13:
                 nq >>= 1
             secs, chk, npq = C.c_double(), C.c_double(), C.c_double()
             L.check(lib.qbx_prim_batch(*cls, K, nq, 42, C.byref(secs), C.byref(chk), C.byref(npq), 0, None, None))
-            tf = (npq.value * pf + nq * hf) / secs.value * 1e-12           # evaluated primitive quartets only
-            cells.append(f"{tf:.2f} ({nq / secs.value * 1e-6:.1f}; {npq.value / (nq * K ** 4) * 100:.0f}%)")
-        kern = "warp-coop2" if nacc >= 180 else "thread"
-        print(f"| ({'spd'[cls[0]]}{'spd'[cls[1]]}\\|{'spd'[cls[2]]}{'spd'[cls[3]]}) | {kern} | " + " | ".join(cells) + " |", flush=True)
+            flops = npq.value * pf + nq * hf                                # evaluated primitive quartets only
+            rows.append({"class": "(%s%s|%s%s)" % tuple("spd"[l] for l in cls), "K": K, "kernel": "warp-coop2" if nacc >= 180 else "thread",
+                         "quartets": nq, "seconds": secs.value, "prim_quartets": npq.value, "model_flops": flops,
+                         "tflops_model": flops / secs.value * 1e-12, "frac_of_fp64_peak": flops / secs.value * 1e-12 / peak.value,
+                         "eris_per_sec": nq * ncomp / secs.value, "surviving_prim_share": npq.value / (nq * K ** 4)})
+    return peak.value, rows
+
+
+def main():
+    peak, rows = sweep()
+    print(f"# Synthetic shell-quartet sweep on one B200 (measured FP64 FMA peak {peak:.1f} TFLOP/s)\n")
+    print("Centres uniform in a 10-bohr cube, exponents log-uniform in [0.1, 1e3], coefficients in [-1, 1] (qbx_prim_batch, seed 42).")
+    print("Cells: model TFLOP/s (SURVEY.md 8d flop count over the primitive quartets actually EVALUATED / CUDA-event time of the ERI kernel); in brackets million contracted quartets per second and the share of the K^4 primitive quartets that survive the |K_ab| < 1e-24 primitive-pair cut-off (tight, distant pairs underflow).")
+    print("The 8d model counts a vertical recurrence on both centres; the thread kernels use the cheaper electron-transfer route, so a model rate can exceed the FP64 pipe's executed rate.\n")
+    print("| class | kernel | " + " | ".join(f"K={k}" for k in KS) + " |")
+    print("|---|---|" + "---|" * len(KS))
+    for cls in sorted(set(r["class"] for r in rows), key=lambda c: [r["class"] for r in rows].index(c)):
+        rs = [r for r in rows if r["class"] == cls]
+        cells = [f"{r['tflops_model']:.2f} ({r['quartets'] / r['seconds'] * 1e-6:.1f}; {r['surviving_prim_share'] * 100:.0f}%)" for r in rs]
+        print(f"| {cls.replace('|', chr(92) + '|')} | {rs[0]['kernel']} | " + " | ".join(cells) + " |", flush=True)
 
 
 if __name__ == "__main__":
