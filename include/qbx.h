@@ -84,7 +84,12 @@ QBX_API int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, doubl
  *   screen_tol  Schwarz threshold on sqrt((ab|ab)(cd|cd)); 0 disables screening
  *   mode        0 = stored (packed unique ERIs kept in HBM), 1 = direct (recomputed in
  *               every qbx_fock_build), 2 = dense N^4 tensor (small N / irregular bases)
- *   rank,nranks shard of the cost-balanced shell-quartet list owned by this process */
+ *   rank,nranks shard of the cost-balanced shell-quartet list owned by this process
+ * A basis with functions outside the s/p/d shell classes (l > 2, contractions over several centres) has no shell-quartet
+ * lists: modes 0 and 1 are then served by the dense tensor when it is small (nbf^4 * 8 <= 16 GiB, one rank) and fail with
+ * QBX_ERR_STATE and an explanatory message otherwise.
+ * Thread safety: calls on ONE handle are serialised by a mutex inside the library; different handles may be used from
+ * different host threads only one call at a time (the library has one stream and process-global kernel caches). */
 QBX_API int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank, int nranks);
 
 /* seam 2: = getGcore(HeeI, DJ, DK_m) for m = 0..nmat-1 sharing one DJ

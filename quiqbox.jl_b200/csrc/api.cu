@@ -225,6 +225,9 @@ extern "C" int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes)
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
     qbx_pool_free(d_t);
+    if (!rc && !b->eng)
+        for (int64_t t = 0; t < N * N * N * N; ++t)
+            if (out[t] != out[t]) { qbx_set_error("qbx_eri_tensor: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
     return rc;
 }
 
@@ -244,8 +247,21 @@ extern "C" int qbx_eri_store(qbx_basis *b, double screen_tol, int mode, int rank
     free_store(b);
     b->nranks = nranks;
     if (mode == 2 || !b->eng) {
-        if (nranks != 1) { qbx_set_error("qbx_eri_store: the dense mode does not shard"); return QBX_ERR_ARG; }
         const int64_t N = b->nbf, need = N * N * N * N * (int64_t)sizeof(double);
+        if (!b->eng && mode != 2) {
+            // A basis with functions outside the s/p/d shell classes (l > 2, contractions over two centres) has no shell
+            // quartet lists: the packed store and the direct mode do not exist for it.  Small bases are served by the dense
+            // tensor (same results, documented in qbx.h); a large one gets an error that says so instead of an N^4 allocation
+            // that cannot succeed or a shard request that is silently ignored.
+            if (nranks != 1 || need > ((int64_t)16 << 30)) {
+                qbx_set_error("qbx_eri_store: this basis contains functions outside the s/p/d shell classes (l > 2 or a contraction over "
+                              "several centres), so the packed store / direct mode and the sharding over ranks are not available; the dense "
+                              "fallback needs nbf^4 * 8 = " + std::to_string((long long)(need >> 20)) + " MiB on one GPU (limit 16 GiB). "
+                              "Use mode 2 explicitly on one rank, or remove the irregular functions.");
+                return QBX_ERR_STATE;
+            }
+        }
+        if (nranks != 1) { qbx_set_error("qbx_eri_store: the dense mode does not shard"); return QBX_ERR_ARG; }
         QBX_CUDA(qbx_dmalloc(&b->d_dense, need));
         if (b->eng) rc = b->eng->fill_tensor(b->d_dense, g_stream, b->stats);
         else { rc = qbx_launch_generic_tensor(b->flat, b->d_dense, g_stream); b->stats[0] += 1; }
@@ -426,6 +442,9 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
     qbx_pool_free(dZ); qbx_pool_free(dR); qbx_pool_free(dO);
+    if (!rc)
+        for (int64_t t = 0; t < b->nbf * b->nbf; ++t)
+            if (out[t] != out[t]) { qbx_set_error("qbx_one_body: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
     return rc;
 }
 

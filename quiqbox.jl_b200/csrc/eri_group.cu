@@ -147,8 +147,24 @@ struct GroupArgs {
     int nheavy;                // leading chunks of `order` that are handed out one TASK per warp
 };
 
+// block size / resident blocks the register allocation aims at, per bra class (A/B builds: QBX_NVCC_DEFS)
+#ifndef QBX_GRP_THREADS_S
+#define QBX_GRP_THREADS_S QBX_ERI_THREADS
+#endif
+#ifndef QBX_GRP_THREADS_P
+#define QBX_GRP_THREADS_P QBX_ERI_THREADS
+#endif
+#ifndef QBX_GRP_MINB_S
+#define QBX_GRP_MINB_S 3
+#endif
+#ifndef QBX_GRP_MINB_P
+#define QBX_GRP_MINB_P 2
+#endif
+template <int LA> constexpr int grp_threads() { return LA == 0 ? QBX_GRP_THREADS_S : (LA == 1 ? QBX_GRP_THREADS_P : QBX_ERI_THREADS); }
+template <int LA> constexpr int grp_minb() { return LA == 0 ? QBX_GRP_MINB_S : (LA == 1 ? QBX_GRP_MINB_P : 1); }
+
 template <int LA>
-__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA == 0 ? 3 : (LA == 1 ? 2 : 1))) eri_group_kernel(GroupArgs p)
+__global__ void __launch_bounds__(grp_threads<LA>(), grp_minb<LA>()) eri_group_kernel(GroupArgs p)
 {
     using EC = EriClass<LA, 0, 0, 0>;
     constexpr int NA = NC(LA);
@@ -248,15 +264,15 @@ int launch_group(GroupArgs a, cudaStream_t s)
         int dev = 0, sms = 0, per_sm = 0;
         QBX_CUDA(cudaGetDevice(&dev));
         QBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_group_kernel<LA>, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES));
+        QBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eri_group_kernel<LA>, grp_threads<LA>(), QBX_BOYS_SMEM_BYTES));
         max_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const int need = (a.ntasks + QBX_ERI_THREADS - 1) / QBX_ERI_THREADS;
+    const int need = (a.ntasks + grp_threads<LA>() - 1) / grp_threads<LA>();
     // task-granular hand-out of the heavy chunks only when the launch is short (few chunks per
     // resident warp), i.e. when the tail decides; on a long list the one-task-per-lane mode is
     // ~8 % faster and the tail is filled by the light chunks anyway
-    if ((a.ntasks + 31) / 32 >= 8 * max_blocks * (QBX_ERI_THREADS / 32)) a.nheavy = 0;
-    eri_group_kernel<LA><<<need < max_blocks ? need : max_blocks, QBX_ERI_THREADS, QBX_BOYS_SMEM_BYTES, s>>>(a);
+    if ((a.ntasks + 31) / 32 >= 8 * max_blocks * (grp_threads<LA>() / 32)) a.nheavy = 0;
+    eri_group_kernel<LA><<<need < max_blocks ? need : max_blocks, grp_threads<LA>(), QBX_BOYS_SMEM_BYTES, s>>>(a);
     QBX_CUDA(cudaGetLastError());
     return QBX_OK;
 }

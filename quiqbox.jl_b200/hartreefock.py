@@ -30,7 +30,7 @@ import numpy as np
 from .basis import GTO, MultiOrbitalData, NuclearCluster, nucRepulsion
 
 defaultDS = 0.75            # HartreeFock.jl: damping strength of :DD
-defaultDIISsize = 10
+defaultDIISsize = 15          # HartreeFock.jl:16
 defaultHFmaxStep = 200      # HartreeFock.jl:20
 defaultSCFconfigArgs = ((":DD", ":ADIIS", ":DIIS"), (5e-3, 1e-4, 1e-9))   # :27
 defaultSecConvRatio = (1000.0, 1000.0)                                     # :28

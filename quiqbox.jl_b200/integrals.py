@@ -185,7 +185,7 @@ class DeviceSCF:
     S, Hcore, X, C, D, F, the (D, F, residual) history of the DIIS family -- stays in HBM, the host sees scalars and
     the m x m Gram matrices.  ``eri`` must hold a store (DeviceERI)."""
 
-    def __init__(self, eri: DeviceERI, S, Hcore, history=24):
+    def __init__(self, eri: DeviceERI, S, Hcore, history=36):
         self.eri, self.n, self.cap = eri, eri.basis.nbf, history
         h = C.c_void_p()
         Sf, Hf = np.asfortranarray(S, dtype=np.float64), np.asfortranarray(Hcore, dtype=np.float64)

@@ -163,6 +163,35 @@ def test_h2o2_631g_scf():
         assert r.converged and r.energy[0] == pytest.approx(-187.42063898359095, abs=2.5e-9), mode
 
 
+def test_h2o2_631g_all_13_configurations():
+    """HartreeFock-test.jl:296-352, the 13 HFconfigs (initial x method stages), through runHartreeFock on the GPU (host SCF
+    loop) and -- every third one -- with the SCF step on the device.  Expectations incl. the two documented deviations of
+    the host driver: tests/test_oracle_golden.py::check_h2o2_config."""
+    from test_oracle_golden import check_h2o2_config, h2o2_configs
+    nuc, xyz = h2o2()
+    bs = mol_basis(nuc, xyz, "6-31G")
+    db = qb.DeviceBasis(bs)
+    for k, (name, cfg) in enumerate(h2o2_configs()):
+        r = qb.runHartreeFock((nuc, xyz), db, cfg, screen_tol=1e-14)
+        check_h2o2_config(name, r.energy[0], r.converged)
+        if k % 3 == 1:
+            d = qb.runHartreeFock((nuc, xyz), db, cfg, screen_tol=1e-14, device_scf=True)
+            check_h2o2_config(name, d.energy[0], d.converged)
+
+
+def test_h2o_631g_rhf_uhf_vs_oracle():
+    """BASELINE.json configs[1]: H2O/6-31G RHF and UHF energies against the oracle's own SCF (tests/golden/oracle_energies.json)."""
+    g = json.load(open(os.path.join(HERE, "golden", "oracle_energies.json")))
+    nuc, xyz = h2o()
+    bs = mol_basis(nuc, xyz, "6-31G")
+    for hf_, key in ((qb.RCHartreeFock(), "H2O/6-31G/RHF"), (qb.UOHartreeFock(), "H2O/6-31G/UHF")):
+        for mode in ("stored", "direct", "dense"):
+            r = qb.runHartreeFock((nuc, xyz), bs, qb.HFconfig(HF=hf_, initial=":CoreH"), mode=mode, screen_tol=0.0)
+            assert r.converged and sum(r.energy) == pytest.approx(g[key], abs=1e-8), (key, mode)
+        d = qb.runHartreeFock((nuc, xyz), bs, qb.HFconfig(HF=hf_, initial=":CoreH"), device_scf=True, screen_tol=0.0)
+        assert d.converged and sum(d.energy) == pytest.approx(g[key], abs=1e-8), key
+
+
 def test_scf_matches_oracle_scf_with_d_shells():
     # no golden with contracted d shells exists in the reference (SURVEY.md 8c): the oracle SCF is the reference value
     g = json.load(open(os.path.join(HERE, "golden", "oracle_energies.json")))
@@ -456,6 +485,24 @@ def test_irregular_basis_falls_back_to_generic_kernels():
     dm = qb.DeviceBasis(mixed)
     assert dm.info()["class_path"] == 0
     assert np.max(np.abs(qb.elecRepulsions(dm) - oracle.OracleBasis(mixed).eri_tensor())) < 1e-12
+
+
+def test_large_irregular_basis_gets_a_clear_error():
+    """an f function used to turn a requested stored/direct store silently into an N^4 allocation (205 GB at
+    N = 400) and to ignore the shard request.  Now: a clear QBX_ERR_STATE; small irregular bases keep the dense fallback."""
+    from quiqbox_b200 import lib as L
+    nuc, xyz = water_cluster(9)
+    bs = mol_basis(nuc, xyz, "cc-pVDZ")                                     # 225 functions: 225^4 * 8 = 20.5 GB > 16 GiB
+    bs.append(qb.genGaussTypeOrb(xyz[0], 1.1, (1, 1, 1)))
+    db = qb.DeviceBasis(bs)
+    assert db.info()["class_path"] == 0
+    for mode in ("stored", "direct"):
+        with pytest.raises(L.QbxError, match="outside the s/p/d shell classes"):
+            qb.DeviceERI(db, mode=mode)
+    small = mol_basis(*h2o(), "6-31G") + [qb.genGaussTypeOrb((0.0, 0.0, 0.0), 1.1, (1, 1, 1))]
+    with pytest.raises(L.QbxError, match="sharding over ranks"):
+        qb.DeviceERI(small, mode="stored", rank=0, nranks=2)
+    qb.DeviceERI(small, mode="stored")                                      # dense fallback, as documented
 
 
 def test_allocation_pool_reuse_and_trim():
