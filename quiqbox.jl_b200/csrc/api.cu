@@ -110,7 +110,8 @@ template <class T>
 static int to_device(T **dst, const std::vector<T> &src)
 {
     QBX_CUDA(qbx_dmalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
-    if (!src.empty()) QBX_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // enqueued: `src` is a member of the handle and outlives the copy; every later use is on the same stream
+    if (!src.empty()) QBX_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
     return QBX_OK;
 }
 
@@ -165,6 +166,7 @@ extern "C" int qbx_basis_destroy(qbx_basis *b)
 {
     if (!b) return QBX_OK;
     if (g_device >= 0) cudaSetDevice(g_device);
+    QbxPoolFreeScope one_sync;
     free_store(b);
     qbx_pool_free(b->flat.cen); qbx_pool_free(b->flat.xpn); qbx_pool_free(b->flat.ang);
     qbx_pool_free(b->flat.bf_off); qbx_pool_free(b->flat.bf_prim); qbx_pool_free(b->flat.bf_w);
@@ -387,17 +389,21 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
     if (b->mode == 0 || b->mode == 1) {
         // the packed-store digestion is only valid for symmetric densities (include/qbx.h); reject anything else here
         // instead of returning a mode-dependent result
-        const int64_t N = b->nbf;
+        const int64_t N = b->nbf, T = 32;                        // tiles: both D[i,j] and D[j,i] stay in cache
         for (int m = 0; m <= nmat; ++m) {
             const double *D = m == 0 ? DJ : DK + (size_t)(m - 1) * N * N;
-            for (int64_t j = 0; j < N; ++j)
-                for (int64_t i = 0; i < j; ++i) {
-                    const double v = D[i + N * j], w = D[j + N * i];
-                    if (!(fabs(v - w) <= 1e-10 * std::max(1.0, std::max(fabs(v), fabs(w))))) {
-                        qbx_set_error("qbx_fock_build: DJ and DK must be symmetric matrices (stored and direct modes)");
-                        return QBX_ERR_ARG;
-                    }
-                }
+            bool ok = true;
+            for (int64_t j0 = 0; j0 < N; j0 += T)
+                for (int64_t i0 = 0; i0 <= j0; i0 += T)
+                    for (int64_t j = j0; j < std::min(N, j0 + T); ++j)
+                        for (int64_t i = i0; i < std::min(j, i0 + T); ++i) {
+                            const double v = D[i + N * j], w = D[j + N * i];
+                            ok &= fabs(v - w) <= 1e-10 * std::max(1.0, std::max(fabs(v), fabs(w)));   // (false for NaN)
+                        }
+            if (!ok) {
+                qbx_set_error("qbx_fock_build: DJ and DK must be symmetric matrices (stored and direct modes)");
+                return QBX_ERR_ARG;
+            }
         }
     }
     if (b->staged_nmat < nmat) {

@@ -96,6 +96,20 @@ double qbx_model_flops_hrr(int la, int lb, int lc, int ld)
     return h;
 }
 
+// QBX_TRACE=2: stream synchronisation + elapsed time since the previous mark, on stderr (finds the slow enqueue-only step)
+static void trace_mark(cudaStream_t s, const char *what, int a = -1, int b = -1)
+{
+    static const bool on = getenv("QBX_TRACE") && atoi(getenv("QBX_TRACE")) >= 2;
+    if (!on) return;
+    static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "    [qbx mark] %-22s %2d %2d  host %.3f ms  + device drain %.3f ms\n", what, a, b,
+            1e3 * std::chrono::duration<double>(t0 - last).count(), 1e3 * std::chrono::duration<double>(t1 - t0).count());
+    last = std::chrono::steady_clock::now();
+}
+
 // QBX_TRACE=1: host-side phase times on stderr
 namespace {
 struct TraceScope {
@@ -239,16 +253,24 @@ __global__ void k_fill_tasks(const double *Qb, const double *Qk, int nb, int nk,
     const int jmax = same ? i + 1 : nk;
     const double qi = Qb[i];
     int64_t g = rowoff[i];
-    for (int j0 = 0; j0 < jmax; j0 += 32) {
-        const int j = j0 + lane;
-        const bool pass = j < jmax && qi * Qk[j] >= tol;
-        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-            const int64_t gg = g + __popc(mask & ((1u << lane) - 1u));
-            const int64_t c = gg / QBX_TASK_CHUNK;
-            if (c % nranks == rank) tasks[(c / nranks) * QBX_TASK_CHUNK + gg % QBX_TASK_CHUNK] = make_int2(i, j);
+    // four windows of 32 kets per trip: the loads are issued together (a row is one warp walking serially over up to
+    // ~8000 kets; with one load in flight per trip the 21 fill kernels of a store were pure latency)
+    for (int j0 = 0; j0 < jmax; j0 += 128) {
+        double q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u + lane; q[u] = j < jmax ? Qk[j] : -1.0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u + lane;
+            const bool pass = j < jmax && qi * q[u] >= tol;
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const int64_t gg = g + __popc(mask & ((1u << lane) - 1u));
+                const int64_t c = gg / QBX_TASK_CHUNK;
+                if (c % nranks == rank) tasks[(c / nranks) * QBX_TASK_CHUNK + gg % QBX_TASK_CHUNK] = make_int2(i, j);
+            }
+            g += __popc(mask);
         }
-        g += __popc(mask);
     }
 }
 
@@ -465,52 +487,64 @@ Engine *Engine::from_shells(const std::vector<HostShell> &shells, int64_t nbf, b
     return e;
 }
 
-// Primitive-pair records of one pair class, computed on the device (k_pair_count / k_pair_fill): the host uploads the
-// shell table, reads back one int per shell pair, sorts the pairs by it and the fill kernel writes the AoS and SoA
-// copies in place.  [The host-thread variant of round 1 -- 6 of the 7 ms of qbx_basis_create -- was deleted after the
-// A/B of round 2: host-buffer step 52.1 -> 49.1 ms, profiles/r02/probe_ab_head_of_round1.log.]
-static int build_pairset_device(const std::vector<HostShell> &sh, const DevShells &S, int la, int lb,
-                                const std::vector<std::pair<int, int>> &sp, bool sort_by_nprim, DevPairSet &out,
-                                std::vector<int2> &shells, cudaStream_t s)
+// Primitive-pair records of the pair classes, computed on the device (k_pair_count / k_pair_fill) in two enqueue-only
+// phases, so that a qbx_basis_create waits for the device twice and not twice per class: `count` uploads the shell
+// pairs and counts their primitive pairs; after the ONE read-back the host sorts the pairs of every class by that
+// count and `fill` writes the AoS and SoA records in place.  [The host-thread variant of round 1 -- 6 of the 7 ms of
+// qbx_basis_create -- was deleted after the A/B of round 2: host-buffer step 52.1 -> 49.1 ms,
+// profiles/r02/probe_ab_head_of_round1.log.]
+struct PairBuild {
+    std::vector<int2> sp0, shells, soa_idx;     // host copies stay alive until the stream has been synchronised
+    std::vector<int> cnt, poff;
+    int2 *d_sp = nullptr;
+    int *d_cnt = nullptr;
+};
+
+static int pairset_count(const DevShells &S, const std::vector<std::pair<int, int>> &sp, PairBuild &w, cudaStream_t s)
 {
-    (void)sh;
     const size_t np_ = sp.size();
+    const double pref = sqrt(2.0) * pow(M_PI, 1.25);
+    w.sp0.resize(np_);
+    for (size_t i = 0; i < np_; ++i) w.sp0[i] = make_int2(sp[i].first, sp[i].second);
+    w.cnt.assign(np_, 0);
+    QBX_CUDA(qbx_dmalloc(&w.d_sp, std::max<size_t>(1, np_) * sizeof(int2)));
+    QBX_CUDA(qbx_dmalloc(&w.d_cnt, std::max<size_t>(1, np_) * sizeof(int)));
+    if (np_) {
+        QBX_CUDA(cudaMemcpyAsync(w.d_sp, w.sp0.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        k_pair_count<<<(unsigned)((np_ + 127) / 128), 128, 0, s>>>(S, w.d_sp, (int)np_, pref, w.d_cnt);
+        QBX_CUDA(cudaMemcpyAsync(w.cnt.data(), w.d_cnt, np_ * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    return QBX_OK;
+}
+
+static int pairset_fill(const DevShells &S, int la, int lb, bool sort_by_nprim, PairBuild &w, DevPairSet &out, cudaStream_t s)
+{
+    const size_t np_ = w.sp0.size();
     out.la = la; out.lb = lb; out.npair = (int)np_; out.nprim = 0;
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
-    std::vector<int2> sp0(np_);
-    for (size_t i = 0; i < np_; ++i) sp0[i] = make_int2(sp[i].first, sp[i].second);
-    std::vector<int> cnt(np_, 0);
-    int2 *d_sp = nullptr; int *d_cnt = nullptr;
-    QBX_CUDA(qbx_dmalloc(&d_sp, std::max<size_t>(1, np_) * sizeof(int2)));
-    QBX_CUDA(qbx_dmalloc(&d_cnt, std::max<size_t>(1, np_) * sizeof(int)));
-    if (np_) {
-        QBX_CUDA(cudaMemcpyAsync(d_sp, sp0.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
-        k_pair_count<<<(unsigned)((np_ + 127) / 128), 128, 0, s>>>(S, d_sp, (int)np_, pref, d_cnt);
-        QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, np_ * sizeof(int), cudaMemcpyDeviceToHost, s));
-        QBX_CUDA(cudaStreamSynchronize(s));                  // the one read-back: primitive pairs per shell pair
-    }
+    const std::vector<int> &cnt = w.cnt;
     std::vector<int> order(np_);
     std::iota(order.begin(), order.end(), 0);
     if (sort_by_nprim)
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
-    shells.assign(np_, make_int2(0, 0));
-    std::vector<int> poff(np_ + 1, 0);
+    w.shells.assign(np_, make_int2(0, 0));
+    w.poff.assign(np_ + 1, 0);
     out.h_nprim.resize(np_);
     for (size_t n = 0; n < np_; ++n) {
-        shells[n] = sp0[order[n]];
+        w.shells[n] = w.sp0[order[n]];
         out.h_nprim[n] = cnt[order[n]];
-        poff[n + 1] = poff[n] + cnt[order[n]];
+        w.poff[n + 1] = w.poff[n] + cnt[order[n]];
     }
-    out.nprim = poff[np_];
-    const size_t n_prim = 8 * (size_t)poff[np_], n_soa = (size_t)QBX_SOA_NF * poff[np_];
-    std::vector<int2> soa_idx(np_);
+    out.nprim = w.poff[np_];
+    const size_t n_prim = 8 * (size_t)w.poff[np_], n_soa = (size_t)QBX_SOA_NF * w.poff[np_];
+    w.soa_idx.resize(np_);
     {
         size_t base = 0, g0 = 0;
         while (g0 < np_) {
             size_t g1 = g0;
             while (g1 < np_ && out.h_nprim[g1] == out.h_nprim[g0]) ++g1;
             const size_t g = g1 - g0;
-            for (size_t j = g0; j < g1; ++j) soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
+            for (size_t j = g0; j < g1; ++j) w.soa_idx[j] = make_int2((int)(base + (j - g0)), (int)g);
             base += g * (size_t)out.h_nprim[g0] * QBX_SOA_NF;
             g0 = g1;
         }
@@ -518,25 +552,28 @@ static int build_pairset_device(const std::vector<HostShell> &sh, const DevShell
     QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa) * sizeof(double)));
     QBX_CUDA(qbx_dmalloc(&out.soa_idx, std::max<size_t>(1, np_) * sizeof(int2)));
     QBX_CUDA(qbx_dmalloc(&out.shells, std::max<size_t>(1, np_) * sizeof(int2)));
-    QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
+    QBX_CUDA(qbx_dmalloc(&out.prim_off, w.poff.size() * sizeof(int)));
     QBX_CUDA(qbx_dmalloc(&out.geom, std::max<size_t>(1, 8 * np_) * sizeof(double)));
     QBX_CUDA(qbx_dmalloc(&out.prim, std::max<size_t>(1, n_prim) * sizeof(double)));
     QBX_CUDA(qbx_dmalloc(&out.schwarz, std::max<size_t>(1, np_) * sizeof(double)));
-    QBX_CUDA(cudaMemcpyAsync(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    QBX_CUDA(cudaMemcpyAsync(out.prim_off, w.poff.data(), w.poff.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     if (np_) {
-        QBX_CUDA(cudaMemcpyAsync(out.soa_idx, soa_idx.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
-        QBX_CUDA(cudaMemcpyAsync(out.shells, shells.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaMemcpyAsync(out.soa_idx, w.soa_idx.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
+        QBX_CUDA(cudaMemcpyAsync(out.shells, w.shells.data(), np_ * sizeof(int2), cudaMemcpyHostToDevice, s));
         k_pair_fill<<<(unsigned)((np_ + 127) / 128), 128, 0, s>>>(S, out.shells, (int)np_, pref, out.prim_off, out.soa_idx, out.prim,
                                                                   out.soa, out.geom);
         QBX_CUDA(cudaGetLastError());
     }
-    QBX_CUDA(cudaStreamSynchronize(s));                      // the host vectors above go out of scope
-    qbx_pool_free_async(d_sp); qbx_pool_free_async(d_cnt);
+    qbx_pool_free_async(w.d_sp); qbx_pool_free_async(w.d_cnt);
+    w.d_sp = nullptr; w.d_cnt = nullptr;
     return QBX_OK;
 }
 
 int Engine::upload(bool pair_adjacent)
 {
+    // Everything below is enqueued on the library's stream from host vectors that live until the end of this function;
+    // the host waits for the device three times: primitive-pair counts, group counts, end.
+    cudaStream_t st = qbx_stream();
     const size_t ns = shells_.size();
     std::vector<int> bf(6 * ns);
     std::vector<double> sc(6 * ns);
@@ -544,8 +581,8 @@ int Engine::upload(bool pair_adjacent)
         for (int c = 0; c < 6; ++c) { bf[6 * s + c] = shells_[s].bf[c]; sc[6 * s + c] = shells_[s].scale[c]; }
     QBX_CUDA(qbx_dmalloc(&d_shell_bf_, std::max<size_t>(1, bf.size()) * sizeof(int)));
     QBX_CUDA(qbx_dmalloc(&d_shell_scale_, std::max<size_t>(1, sc.size()) * sizeof(double)));
-    QBX_CUDA(cudaMemcpy(d_shell_bf_, bf.data(), bf.size() * sizeof(int), cudaMemcpyHostToDevice));
-    QBX_CUDA(cudaMemcpy(d_shell_scale_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    QBX_CUDA(cudaMemcpyAsync(d_shell_bf_, bf.data(), bf.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    QBX_CUDA(cudaMemcpyAsync(d_shell_scale_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     std::vector<int> first(ns), ext;
     for (size_t s = 0; s < ns; ++s) {
         first[s] = (int)ext.size();
@@ -554,8 +591,8 @@ int Engine::upload(bool pair_adjacent)
     nint_ = (int64_t)ext.size();
     QBX_CUDA(qbx_dmalloc(&d_shell_first_, std::max<size_t>(1, ns) * sizeof(int)));
     QBX_CUDA(qbx_dmalloc(&d_ext_of_int_, std::max<size_t>(1, ext.size()) * sizeof(int)));
-    QBX_CUDA(cudaMemcpy(d_shell_first_, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice));
-    QBX_CUDA(cudaMemcpy(d_ext_of_int_, ext.data(), ext.size() * sizeof(int), cudaMemcpyHostToDevice));
+    QBX_CUDA(cudaMemcpyAsync(d_shell_first_, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    QBX_CUDA(cudaMemcpyAsync(d_ext_of_int_, ext.data(), ext.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     std::vector<std::pair<int, int>> sp[QBX_NPAIRCLS];
     if (pair_adjacent) {
         for (size_t s = 0; s + 1 < ns; s += 2) {
@@ -575,9 +612,9 @@ int Engine::upload(bool pair_adjacent)
     { int acc = 0; for (size_t s = 0; s < ns; ++s) { first_h[s] = acc; acc += qbx_nc(shells_[s].l); } }
     DevShells S{nullptr, nullptr, nullptr, nullptr};
     void *d_tab[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> cen(3 * ns), xp, cf;
+    std::vector<int> xoff(ns + 1, 0);
     {
-        std::vector<double> cen(3 * ns), xp, cf;
-        std::vector<int> xoff(ns + 1, 0);
         for (size_t i = 0; i < ns; ++i) {
             for (int d = 0; d < 3; ++d) cen[3 * i + d] = shells_[i].cen[d];
             xp.insert(xp.end(), shells_[i].xpn.begin(), shells_[i].xpn.end());
@@ -588,29 +625,42 @@ int Engine::upload(bool pair_adjacent)
         const void *src[4] = {cen.data(), xoff.data(), xp.data(), cf.data()};
         for (int i = 0; i < 4; ++i) {
             QBX_CUDA(qbx_pool_malloc(&d_tab[i], std::max<size_t>(8, bytes[i])));
-            if (bytes[i]) QBX_CUDA(cudaMemcpy(d_tab[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+            if (bytes[i]) QBX_CUDA(cudaMemcpyAsync(d_tab[i], src[i], bytes[i], cudaMemcpyHostToDevice, st));
         }
         S = DevShells{(const double *)d_tab[0], (const int *)d_tab[1], (const double *)d_tab[2], (const double *)d_tab[3]};
     }
-    for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
-        // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
-        // equal-count group a run of pairs shares A and walks over consecutive B
-        std::vector<int2> sh;
-        int rc = build_pairset_device(shells_, S, kClsLa[pc], kClsLb[pc], sp[pc], !pair_adjacent, pairs_[pc], sh, qbx_stream());
-        if (rc) return rc;
-        {
+    PairBuild work[QBX_NPAIRCLS];
+    std::vector<int4> info[QBX_NPAIRCLS];
+    int rc;
+    {
+        TraceScope trc("create: pair counts");
+        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc)
+            if ((rc = pairset_count(S, sp[pc], work[pc], st))) return rc;
+        QBX_CUDA(cudaStreamSynchronize(st));                 // read-back 1: primitive pairs per shell pair, all classes
+    }
+    {
+        TraceScope trf("create: pair fill (enqueue)");
+        for (int pc = 0; pc < QBX_NPAIRCLS; ++pc) {
+            // sorted by primitive count (stable): ties keep the (A major, B ascending) order, so inside an
+            // equal-count group a run of pairs shares A and walks over consecutive B
             DevPairSet &P = pairs_[pc];
-            std::vector<int4> info(P.npair);
-            for (int i = 0; i < P.npair; ++i) info[i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
-            QBX_CUDA(qbx_dmalloc(&P.info, std::max<size_t>(1, info.size()) * sizeof(int4)));
-            if (P.npair) QBX_CUDA(cudaMemcpy(P.info, info.data(), info.size() * sizeof(int4), cudaMemcpyHostToDevice));
-            // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
-            if (pc == 0 && !pair_adjacent && P.npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
-                TraceScope trg("group build");
-                if ((rc = qbx_group_build(shells_, sh, groups_, P.shells))) return rc;
-                use_groups_ = groups_.ng > 0 && groups_.ng < P.npair;     // only when something is shared
-            }
+            if ((rc = pairset_fill(S, kClsLa[pc], kClsLb[pc], !pair_adjacent, work[pc], P, st))) return rc;
+            const std::vector<int2> &sh = work[pc].shells;
+            info[pc].resize(P.npair);
+            for (int i = 0; i < P.npair; ++i) info[pc][i] = make_int4(sh[i].x, sh[i].y, first_h[sh[i].x], first_h[sh[i].y]);
+            QBX_CUDA(qbx_dmalloc(&P.info, std::max<size_t>(1, info[pc].size()) * sizeof(int4)));
+            if (P.npair) QBX_CUDA(cudaMemcpyAsync(P.info, info[pc].data(), info[pc].size() * sizeof(int4), cudaMemcpyHostToDevice, st));
         }
+    }
+    // ket-side general-contraction sharing for the (xs|ss) classes (QBX_GC=0 switches it off)
+    if (!pair_adjacent && pairs_[0].npair && !(getenv("QBX_GC") && atoi(getenv("QBX_GC")) == 0)) {
+        TraceScope trg("create: group build");
+        if ((rc = qbx_group_build(shells_, work[0].shells, groups_, pairs_[0].shells))) return rc;
+        use_groups_ = groups_.ng > 0 && groups_.ng < pairs_[0].npair;     // only when something is shared
+    }
+    {
+        TraceScope trs("create: final sync");
+        QBX_CUDA(cudaStreamSynchronize(st));                 // the host vectors above go out of scope
     }
     for (void *p : d_tab) qbx_pool_free_async(p);
     QBX_CUDA(cudaEventCreate(&ev0_));
@@ -620,6 +670,7 @@ int Engine::upload(bool pair_adjacent)
 
 Engine::~Engine()
 {
+    QbxPoolFreeScope one_sync;
     release_store();
     qbx_group_free(groups_);
     for (auto &p : pairs_) { qbx_pool_free(p.shells); qbx_pool_free(p.prim_off); qbx_pool_free(p.geom); qbx_pool_free(p.prim); qbx_pool_free(p.schwarz); qbx_pool_free(p.soa); qbx_pool_free(p.soa_idx); qbx_pool_free(p.info); }
@@ -635,6 +686,7 @@ Engine::~Engine()
 
 void Engine::release_store()
 {
+    QbxPoolFreeScope one_sync;
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
             qbx_pool_free(tasks_[b][k].tasks); qbx_pool_free(tasks_[b][k].gt_bra); qbx_pool_free(tasks_[b][k].gt_grp); qbx_pool_free(tasks_[b][k].gt_off); qbx_pool_free(tasks_[b][k].order);
@@ -762,7 +814,9 @@ int Engine::tasks_fill(int bc, int kc, double tol, int rank, int nranks, bool gr
     int rc = QBX_OK;
     if (B.npair == 0 || K.npair == 0) return QBX_OK;
     if (grp) {
+        trace_mark(s, "(before group fill)", bc, kc);
         rc = qbx_group_fill(groups_, B, K, bc == kc, tol, rank, nranks, ts, h_total, out, d_stat, d_nheavy, s);
+        trace_mark(s, "group_fill", bc, kc);
     } else {
         const int64_t total = h_total[0];
         const int64_t nfull = total / QBX_TASK_CHUNK, rem = total % QBX_TASK_CHUNK;
@@ -775,9 +829,12 @@ int Engine::tasks_fill(int bc, int kc, double tol, int rank, int nranks, bool gr
             const int64_t threads = (int64_t)B.npair * 32;
             k_fill_tasks<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(B.schwarz, K.schwarz, B.npair, K.npair, bc == kc, tol,
                                                                            ts.off[0], rank, nranks, out.tasks);
+            trace_mark(s, "fill_tasks", bc, kc);
             k_task_cost<<<296, 256, 0, s>>>(out.tasks, mine, B.prim_off, K.prim_off, d_stat + 1);
             QBX_CUDA(cudaGetLastError());
+            trace_mark(s, "task_cost", bc, kc);
             if (want_order) rc = qbx_chunk_order(out.tasks, nullptr, nullptr, mine, B.prim_off, K.prim_off, &out.order, nullptr, s);
+            trace_mark(s, "chunk_order", bc, kc);
         }
     }
     for (int i = 0; i < 3; ++i) { qbx_pool_free_async(ts.cnt[i]); qbx_pool_free_async(ts.off[i]); }
@@ -857,13 +914,23 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
     QBX_CUDA(qbx_dmalloc(&d_plan, plan_bytes));
     QBX_CUDA(cudaMemsetAsync(d_plan, 0, plan_bytes, s));
     TaskScratch scratch[QBX_NCLASS];
+    // The 21 classes are independent and their list kernels are small (a warp per bra row): they go round-robin over
+    // the side streams, in both phases, so that the device overlaps them instead of draining ~190 launches one by one.
+    // Scratch blocks freed meanwhile are held back until the streams have been joined (QbxPoolDeferScope).
+    static const bool trace2 = getenv("QBX_TRACE") && atoi(getenv("QBX_TRACE")) >= 2;     // per-step marks need one stream
+    const bool spread = !trace2;
+    if (spread && (rc = fork(s))) return rc;
     {
+        QbxPoolDeferScope held;
         int c = 0;
         for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
             for (int kc = 0; kc <= bc; ++kc, ++c)
                 if ((rc = tasks_count(bc, kc, tol, rank, nranks, mode == 0 && grouped(bc, kc), scratch[c],
-                                      (int64_t *)d_plan + 3 * c, s)))
+                                      (int64_t *)d_plan + 3 * c, spread ? side_[c % kSide] : s))) {
+                    if (spread) join(s);
                     return rc;
+                }
+        if (spread && (rc = join(s))) return rc;
     }
     QBX_CUDA(cudaMemcpyAsync(h_plan, d_plan, o_stat, cudaMemcpyDeviceToHost, s));
     QBX_CUDA(cudaStreamSynchronize(s));                       // host sync 1 of 2: list sizes
@@ -872,13 +939,19 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
     auto T1b = now();
     t_tasks = secs(T1, T1b);
     {
+        QbxPoolDeferScope held;
+        if (spread && (rc = fork(s))) return rc;
         int c = 0;
         for (int bc = 0; bc < QBX_NPAIRCLS; ++bc)
             for (int kc = 0; kc <= bc; ++kc, ++c) {
                 if ((rc = tasks_fill(bc, kc, tol, rank, nranks, mode == 0 && grouped(bc, kc), mode == 0, scratch[c], totals + 3 * c,
-                                     tasks_[bc][kc], (double *)(d_plan + o_stat) + 2 * c, (int *)(d_plan + o_nh) + c, s)))
+                                     tasks_[bc][kc], (double *)(d_plan + o_stat) + 2 * c, (int *)(d_plan + o_nh) + c,
+                                     spread ? side_[c % kSide] : s))) {
+                    if (spread) join(s);
                     return rc;
+                }
                 const TaskList &tl = tasks_[bc][kc];
+                trace_mark(s, "(before vals alloc)", bc, kc);
                 if (mode == 0 && tl.n > 0) {
                     const size_t bytes = (size_t)tl.n * qbx_class_ops(bc, kc)->ncomp * sizeof(double);
                     if (qbx_dmalloc(&vals_[bc][kc], bytes) != cudaSuccess) {
@@ -890,6 +963,8 @@ int Engine::store(double tol, int mode, int rank, int nranks, cudaStream_t s, do
                     stored_bytes_ += (int64_t)bytes;
                 }
             }
+        if (spread && (rc = join(s))) return rc;
+        held.release();
     }
     QBX_CUDA(cudaMemcpyAsync(h_plan + o_stat, d_plan + o_stat, plan_bytes - o_stat, cudaMemcpyDeviceToHost, s));
     QBX_CUDA(cudaStreamSynchronize(s));                       // host sync 2 of 2: statistics, heavy-chunk counts

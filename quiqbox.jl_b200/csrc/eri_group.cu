@@ -387,19 +387,22 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         }
     }
     // 2. group pairs and their members (regular pair indices)
-    std::map<std::pair<int, int>, int> gp_index;
+    const size_t npg = pgs.size();
+    std::vector<int> gp_index(npg * npg, -1);                // (P, Q) -> group pair, in order of first appearance
     std::vector<std::vector<int>> members;
     std::vector<std::pair<int, int>> gp_pq;
+    members.reserve(npg * (npg + 1) / 2);
     for (size_t j = 0; j < ss_pairs.size(); ++j) {
         int P = pg_of[ss_pairs[j].x], Q = pg_of[ss_pairs[j].y];
         if (P < Q) std::swap(P, Q);
-        auto it = gp_index.find({P, Q});
-        if (it == gp_index.end()) {
-            it = gp_index.emplace(std::make_pair(P, Q), (int)members.size()).first;
+        int &gi = gp_index[(size_t)P * npg + Q];
+        if (gi < 0) {
+            gi = (int)members.size();
             members.emplace_back();
+            members.back().reserve(QBX_GRP_MAXMEM);
             gp_pq.push_back({P, Q});
         }
-        members[it->second].push_back((int)j);
+        members[gi].push_back((int)j);
     }
     const size_t ng0 = members.size();
     for (auto &m : members)

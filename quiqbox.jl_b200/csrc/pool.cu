@@ -69,9 +69,14 @@ cudaError_t qbx_pool_malloc(void **p, size_t bytes)
     return e;
 }
 
+static thread_local int tl_free_scope = 0;
+QbxPoolFreeScope::QbxPoolFreeScope() { if (tl_free_scope++ == 0) cudaDeviceSynchronize(); }
+QbxPoolFreeScope::~QbxPoolFreeScope() { --tl_free_scope; }
+
 static cudaError_t pool_free(void *p, bool sync)
 {
     if (!p) return cudaSuccess;
+    if (tl_free_scope > 0) sync = false;
     Pool &P = g_pool;
     std::lock_guard<std::mutex> lk(P.mu);
     auto it = P.size_of.find(p);
@@ -94,7 +99,23 @@ cudaError_t qbx_pool_free(void *p) { return pool_free(p, true); }
 // block is ordered after the work enqueued so far.  That holds inside the library because all of
 // it runs on the library's one stream (side streams fork from and join into it) and
 // qbx_set_stream synchronises the device when the stream changes.
-cudaError_t qbx_pool_free_async(void *p) { return pool_free(p, false); }
+static thread_local std::vector<void *> *tl_deferred = nullptr;
+cudaError_t qbx_pool_free_async(void *p)
+{
+    if (p && tl_deferred) { tl_deferred->push_back(p); return cudaSuccess; }
+    return pool_free(p, false);
+}
+
+QbxPoolDeferScope::QbxPoolDeferScope() { if (!tl_deferred) tl_deferred = new std::vector<void *>(); }
+QbxPoolDeferScope::~QbxPoolDeferScope() { release(); }
+void QbxPoolDeferScope::release()
+{
+    if (!tl_deferred) return;
+    std::vector<void *> *list = tl_deferred;
+    tl_deferred = nullptr;
+    for (void *p : *list) pool_free(p, false);
+    delete list;
+}
 
 // Pinned host scratch for the small read-backs (counts, totals); grows, never shrinks.
 void *qbx_pinned(size_t bytes)

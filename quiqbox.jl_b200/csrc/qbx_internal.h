@@ -34,6 +34,24 @@ void qbx_set_error(const std::string &msg);
 cudaError_t qbx_pool_malloc(void **p, size_t bytes);
 cudaError_t qbx_pool_free(void *p);
 cudaError_t qbx_pool_free_async(void *p);
+// One device synchronisation for a batch of qbx_pool_free calls (a handle's destructor returns ~100 blocks): while a
+// scope is alive on this thread qbx_pool_free does not synchronise again.  Nothing may be enqueued inside the scope.
+struct QbxPoolFreeScope {
+    QbxPoolFreeScope();
+    ~QbxPoolFreeScope();
+    QbxPoolFreeScope(const QbxPoolFreeScope &) = delete;
+    QbxPoolFreeScope &operator=(const QbxPoolFreeScope &) = delete;
+};
+// While a scope is alive on this thread qbx_pool_free_async only remembers the blocks; release() returns them to the
+// pool.  For phases that run on the side streams: a block freed by one stream must not be handed to another before the
+// streams have been joined (release() is called after the join has been enqueued).
+struct QbxPoolDeferScope {
+    QbxPoolDeferScope();
+    ~QbxPoolDeferScope();               // releases if release() was not called
+    void release();
+    QbxPoolDeferScope(const QbxPoolDeferScope &) = delete;
+    QbxPoolDeferScope &operator=(const QbxPoolDeferScope &) = delete;
+};
 void *qbx_pinned(size_t bytes);
 void *qbx_staging(size_t bytes);
 std::mutex &qbx_staging_mutex();
