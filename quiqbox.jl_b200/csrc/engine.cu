@@ -524,9 +524,17 @@ static int pairset_fill(const DevShells &S, int la, int lb, bool sort_by_nprim, 
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
     const std::vector<int> &cnt = w.cnt;
     std::vector<int> order(np_);
-    std::iota(order.begin(), order.end(), 0);
-    if (sort_by_nprim)
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+    if (sort_by_nprim) {
+        // stable, descending count: a counting sort (the counts are at most K_a * K_b, a few hundred)
+        int cmax = 0;
+        for (int c : cnt) cmax = std::max(cmax, c);
+        std::vector<int> start(cmax + 2, 0);
+        for (int c : cnt) ++start[cmax - c + 1];
+        for (int c = 0; c <= cmax; ++c) start[c + 1] += start[c];
+        for (size_t i = 0; i < np_; ++i) order[start[cmax - cnt[i]]++] = (int)i;
+    } else {
+        std::iota(order.begin(), order.end(), 0);
+    }
     w.shells.assign(np_, make_int2(0, 0));
     w.poff.assign(np_ + 1, 0);
     out.h_nprim.resize(np_);
@@ -605,6 +613,7 @@ int Engine::upload(bool pair_adjacent)
         // first shell, which the digestion's segmented warp sums rely on (digest.cuh).  [Listing the pairs diagonal
         // by diagonal, so that the 32 kets of a warp hold 32 different shells C and D, was measured in round 2
         // and lost: it needs 32 shells of one kind, (H2O)16 has 16 -- profiles/r02/digest_history.md.]
+        for (auto &v : sp) v.reserve(ns * (ns + 1) / 2);
         for (size_t a = 0; a < ns; ++a)
             for (size_t b = 0; b <= a; ++b) sp[pair_cls(shells_[a].l, shells_[b].l)].push_back({(int)a, (int)b});
     }

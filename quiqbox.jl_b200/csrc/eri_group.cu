@@ -389,30 +389,30 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
     // 2. group pairs and their members (regular pair indices)
     const size_t npg = pgs.size();
     std::vector<int> gp_index(npg * npg, -1);                // (P, Q) -> group pair, in order of first appearance
-    std::vector<std::vector<int>> members;
+    std::vector<int> members, nmem;                          // flat: QBX_GRP_MAXMEM slots per group pair
     std::vector<std::pair<int, int>> gp_pq;
-    members.reserve(npg * (npg + 1) / 2);
+    members.reserve(npg * (npg + 1) / 2 * QBX_GRP_MAXMEM);
     for (size_t j = 0; j < ss_pairs.size(); ++j) {
         int P = pg_of[ss_pairs[j].x], Q = pg_of[ss_pairs[j].y];
         if (P < Q) std::swap(P, Q);
         int &gi = gp_index[(size_t)P * npg + Q];
         if (gi < 0) {
-            gi = (int)members.size();
-            members.emplace_back();
-            members.back().reserve(QBX_GRP_MAXMEM);
+            gi = (int)nmem.size();
+            nmem.push_back(0);
+            members.resize(members.size() + QBX_GRP_MAXMEM, -1);
             gp_pq.push_back({P, Q});
         }
-        members[gi].push_back((int)j);
+        if (nmem[gi] >= QBX_GRP_MAXMEM) { qbx_set_error("internal: group pair with more than 9 members"); return QBX_ERR_STATE; }
+        members[(size_t)gi * QBX_GRP_MAXMEM + nmem[gi]++] = (int)j;
     }
-    const size_t ng0 = members.size();
-    for (auto &m : members)
-        if (m.size() > QBX_GRP_MAXMEM) { qbx_set_error("internal: group pair with more than 9 members"); return QBX_ERR_STATE; }
+    const size_t ng0 = nmem.size();
     const double pref = sqrt(2.0) * pow(M_PI, 1.25);
     if (ng0 > 0) {
         // ---- records on the device: count -> host sort by count -> fill
         cudaStream_t st = qbx_stream();
         std::vector<double> gcen(3 * pgs.size()), gxpn, scoef;
-        std::vector<int> gxoff(pgs.size() + 1, 0), scoef_off(sh.size() + 1, 0), gmem(ng0 * QBX_GRP_MAXMEM, -1);
+        std::vector<int> gxoff(pgs.size() + 1, 0), scoef_off(sh.size() + 1, 0);
+        const std::vector<int> &gmem = members;
         std::vector<int2> gp(ng0);
         for (size_t g = 0; g < pgs.size(); ++g) {
             for (int d = 0; d < 3; ++d) gcen[3 * g + d] = pgs[g].cen[d];
@@ -423,10 +423,7 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
             scoef.insert(scoef.end(), coef[i].begin(), coef[i].end());
             scoef_off[i + 1] = (int)scoef.size();
         }
-        for (size_t g = 0; g < ng0; ++g) {
-            gp[g] = make_int2(gp_pq[g].first, gp_pq[g].second);
-            for (size_t m = 0; m < members[g].size(); ++m) gmem[g * QBX_GRP_MAXMEM + m] = members[g][m];
-        }
+        for (size_t g = 0; g < ng0; ++g) gp[g] = make_int2(gp_pq[g].first, gp_pq[g].second);
         void *d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         const void *src[8] = {gcen.data(), gxoff.data(), gxpn.data(), scoef_off.data(), scoef.data(), pg_of.data(), gp.data(), gmem.data()};
         const size_t bytes[8] = {gcen.size() * 8, gxoff.size() * 4, gxpn.size() * 8, scoef_off.size() * 4, scoef.size() * 8,
@@ -445,16 +442,22 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         QBX_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, ng0 * sizeof(int), cudaMemcpyDeviceToHost, st));
         QBX_CUDA(cudaStreamSynchronize(st));
         std::vector<int> order(ng0);
-        for (size_t g = 0; g < ng0; ++g) order[g] = (int)g;
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+        {   // stable, descending count (counting sort)
+            int cmax = 0;
+            for (int c : cnt) cmax = std::max(cmax, c);
+            std::vector<int> start(cmax + 2, 0);
+            for (int c : cnt) ++start[cmax - c + 1];
+            for (int c = 0; c <= cmax; ++c) start[c + 1] += start[c];
+            for (size_t g = 0; g < ng0; ++g) order[start[cmax - cnt[g]]++] = (int)g;
+        }
         out.ng = (int)ng0;
         out.h_nprim.resize(ng0); out.h_nmem.resize(ng0);
         std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0);
         for (size_t n = 0; n < ng0; ++n) {
             const int g = order[n];
             out.h_nprim[n] = cnt[g];
-            out.h_nmem[n] = (int)members[g].size();
-            for (size_t m = 0; m < members[g].size(); ++m) mem[n * QBX_GRP_MAXMEM + m] = members[g][m];
+            out.h_nmem[n] = nmem[g];
+            for (int m = 0; m < nmem[g]; ++m) mem[n * QBX_GRP_MAXMEM + m] = members[(size_t)g * QBX_GRP_MAXMEM + m];
             poff[n + 1] = poff[n] + cnt[g];
         }
         std::vector<int2> soa_idx(ng0);
