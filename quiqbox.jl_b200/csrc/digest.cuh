@@ -99,17 +99,28 @@ __device__ __forceinline__ void digest_flush_row(double *Krow, int ic, int id, c
 //   * the block factor f multiplies the sums at flush time, not the values.
 // Values are read once and feed J and K together (the second exchange density of a UHF build
 // re-reads them).
+// (A/B on a B200, tools/gpu_ab_digest.sh, Fock build of (H2O)16: slab 64 / keep 18 -- the round-1 guess -- 12.2 ms;
+// slab 32 11.9, slab 16 12.0, slab 128 12.6; keep 0 14.6, keep 36 11.6, keep 54 11.6; slab 32 + keep 36 11.4 ms.
+// One register tier up or down in digest_min_blocks: 13.9 / 11.85 ms, two down 13.0.)
 #ifndef QBX_DIGEST_SLAB
-#define QBX_DIGEST_SLAB 64
+#define QBX_DIGEST_SLAB 32
 #endif
 #ifndef QBX_DIGEST_KEEP_B
-#define QBX_DIGEST_KEEP_B 18
+#define QBX_DIGEST_KEEP_B 36
 #endif
 
-// resident blocks per SM the register allocation aims at (128 threads each)
+// resident blocks per SM the register allocation aims at (128 threads each), by components per quartet
+// (A/B builds: QBX_NVCC_DEFS="-DQBX_DIGEST_MB2=6"; tools/gpu_ab_digest.sh)
+#ifndef QBX_DIGEST_MB0
+#define QBX_DIGEST_MB0 10
+#define QBX_DIGEST_MB1 6
+#define QBX_DIGEST_MB2 4
+#define QBX_DIGEST_MB3 3
+#define QBX_DIGEST_MB4 2
+#endif
 __host__ __device__ constexpr int digest_min_blocks(int ncomp)
 {
-    return ncomp <= 3 ? 10 : (ncomp <= 9 ? 6 : (ncomp <= 36 ? 4 : (ncomp <= 162 ? 3 : 2)));
+    return ncomp <= 3 ? QBX_DIGEST_MB0 : (ncomp <= 9 ? QBX_DIGEST_MB1 : (ncomp <= 36 ? QBX_DIGEST_MB2 : (ncomp <= 162 ? QBX_DIGEST_MB3 : QBX_DIGEST_MB4)));
 }
 
 // J/K updates of one quartet per lane.  v holds slab 0 of the quartet's values on entry.
