@@ -398,15 +398,20 @@ def main():
             comm = None
             if world > 1:
                 comm = LibComm.__new__(LibComm); comm.rank, comm.size = rank, world        # communicator already initialised above
-            tm = {}
-            t0 = time.perf_counter()
-            hdb = qb.DeviceBasis(bs)
             cfg = qb.HFconfig(initial=":CoreH")
-            r = qb.runHartreeFock((nuc, xyz), hdb, cfg, mode="stored", screen_tol=args.screen, comm=comm, device_scf=True, timings=tm)
-            torch.cuda.synchronize()
-            wall = time.perf_counter() - t0
+            walls = []
+            for _ in range(2):                                 # the first call also loads cuBLAS / cuSOLVER and fills the pool
+                tm = {}
+                t0 = time.perf_counter()
+                hdb = qb.DeviceBasis(bs)
+                r = qb.runHartreeFock((nuc, xyz), hdb, cfg, mode="stored", screen_tol=args.screen, comm=comm, device_scf=True, timings=tm)
+                torch.cuda.synchronize()
+                walls.append(time.perf_counter() - t0)
+                if len(walls) < 2:
+                    hdb.close()
+            wall = walls[-1]
             runhf = {"energy_hartree": float(sum(r.energy)), "converged": bool(r.converged), "steps": int(r.steps),
-                     "fock_builds": int(r.fockBuilds), "wall_seconds": wall,
+                     "fock_builds": int(r.fockBuilds), "wall_seconds": wall, "wall_seconds_first_call_in_process": walls[0],
                      "setup_seconds (basis, one-electron matrices, Schwarz, task lists, all ERIs)": wall - tm["scf_loop_seconds"] - tm["guess_seconds"],
                      "guess_seconds": tm["guess_seconds"], "scf_loop_seconds": tm["scf_loop_seconds"],
                      "device_fock_seconds": tm["device_fock_seconds"], "device_eigen_density_seconds": tm["device_eigen_seconds"],

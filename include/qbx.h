@@ -176,7 +176,8 @@ QBX_API int qbx_pool_trim(int64_t *counts);
 
 /* counters since the last reset: [0] kernels launched, [1] device seconds in ERI kernels,
  * [2] device seconds in digestion kernels, [3] primitive quartets evaluated,
- * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6..15] reserved */
+ * [4] model flops (SURVEY.md 8d counting rule), [5] bytes streamed by digestion, [6] stored-mode Fock builds that ran as
+ * one CUDA-graph launch (a build is captured the second time it sees the same device buffers), [7..15] reserved */
 QBX_API int qbx_stats(qbx_basis *b, double *out, int reset);
 
 /* ---- the SCF step on the device.  getCDFE (src/HartreeFock.jl:392-403) -- solveFockMatrix

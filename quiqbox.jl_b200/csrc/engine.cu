@@ -696,6 +696,8 @@ Engine::~Engine()
 void Engine::release_store()
 {
     QbxPoolFreeScope one_sync;
+    ++store_gen_;
+    drop_fock_graph();
     for (int b = 0; b < QBX_NPAIRCLS; ++b)
         for (int k = 0; k < QBX_NPAIRCLS; ++k) {
             qbx_pool_free(tasks_[b][k].tasks); qbx_pool_free(tasks_[b][k].gt_bra); qbx_pool_free(tasks_[b][k].gt_grp); qbx_pool_free(tasks_[b][k].gt_off); qbx_pool_free(tasks_[b][k].order);
@@ -1097,9 +1099,70 @@ int Engine::class_stats(cudaStream_t s, double *stats, double *out)
     return QBX_OK;
 }
 
+void Engine::drop_fock_graph()
+{
+    if (fock_graph_) { cudaGraphExecDestroy(fock_graph_); fock_graph_ = nullptr; }
+    fock_key_ = FockKey();
+    fock_seen_ = 0;
+}
+
 int Engine::fock(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats)
 {
     if (mode_ != 0 && mode_ != 1) { qbx_set_error("fock: no ERI representation stored"); return QBX_ERR_STATE; }
+    static const bool use_graph = !(getenv("QBX_FOCK_GRAPH") && atoi(getenv("QBX_FOCK_GRAPH")) == 0);
+    if (!use_graph || mode_ != 0 || s == nullptr) return fock_enqueue(nmat, dDJ, dDK, dG, s, stats);
+    const bool same = fock_key_.nmat == nmat && fock_key_.dj == dDJ && fock_key_.dk == dDK && fock_key_.g == dG && fock_key_.s == s &&
+                      fock_key_.gen == store_gen_;
+    if (same && fock_graph_) {
+        if (cudaGraphLaunch(fock_graph_, s) == cudaSuccess) {
+            for (int i = 0; i < 8; ++i) stats[i] += fock_stats_[i];
+            stats[6] += 1;                                     // graph launches (qbx_stats)
+            return QBX_OK;
+        }
+        cudaGetLastError();
+        drop_fock_graph();                                     // replay refused: fall through to the eager path
+    }
+    if (!same) {
+        drop_fock_graph();
+        fock_key_.nmat = nmat; fock_key_.dj = dDJ; fock_key_.dk = dDK; fock_key_.g = dG; fock_key_.s = s; fock_key_.gen = store_gen_;
+    }
+    if (++fock_seen_ < 2) return fock_enqueue(nmat, dDJ, dDK, dG, s, stats);     // a one-off build is not worth a capture
+    // second build with the same buffers: capture it, launch the graph
+    if (!d_bad_) QBX_CUDA(qbx_dmalloc(&d_bad_, sizeof(int)));
+    if (!fork_ev_) { int rc = fork(s); if (rc) return rc; rc = join(s); if (rc) return rc; }     // side streams exist before the capture
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        fock_seen_ = -(1 << 30);                               // never try again on this key
+        return fock_enqueue(nmat, dDJ, dDK, dG, s, stats);
+    }
+    double captured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int rc = fock_enqueue(nmat, dDJ, dDK, dG, s, captured);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+    if (rc != QBX_OK || ee != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        fock_seen_ = -(1 << 30);
+        if (rc != QBX_OK) return rc;
+        return fock_enqueue(nmat, dDJ, dDK, dG, s, stats);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&fock_graph_, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !fock_graph_) {
+        cudaGetLastError();
+        fock_graph_ = nullptr;
+        fock_seen_ = -(1 << 30);
+        return fock_enqueue(nmat, dDJ, dDK, dG, s, stats);
+    }
+    for (int i = 0; i < 8; ++i) fock_stats_[i] = captured[i];
+    QBX_CUDA(cudaGraphLaunch(fock_graph_, s));
+    for (int i = 0; i < 8; ++i) stats[i] += fock_stats_[i];
+    stats[6] += 1;
+    return QBX_OK;
+}
+
+int Engine::fock_enqueue(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats)
+{
     const int64_t NI2 = nint_ * nint_;
     const unsigned pg = (unsigned)((NI2 + 255) / 256);
     double *DJi = d_Dint_, *DKi = d_Dint_ + NI2;

@@ -160,10 +160,23 @@ private:
     double n_primq_ = 0, model_flops_ = 0;
     // the 21 class kernels of a pass are independent: they are dealt over a few side streams so
     // that the tail of one class overlaps the head of the next
-    static constexpr int kSide = 4;
+#ifndef QBX_SIDE_STREAMS
+#define QBX_SIDE_STREAMS 4
+#endif
+    static constexpr int kSide = QBX_SIDE_STREAMS;
     cudaStream_t side_[kSide] = {nullptr};
     cudaEvent_t side_ev_[kSide] = {nullptr}, fork_ev_ = nullptr;
     int fork(cudaStream_t s);
+    // stored-mode Fock build as a CUDA graph: the ~30 launches (permute, clears, 21 digestions over the side streams,
+    // finish) of a build are captured the SECOND time the same (nmat, DJ, DK, G) device pointers are seen on the same
+    // store and replayed from then on -- an SCF calls the build 30 times with fixed buffers.  QBX_FOCK_GRAPH=0: eager.
+    cudaGraphExec_t fock_graph_ = nullptr;
+    struct FockKey { int nmat = 0; const void *dj = nullptr, *dk = nullptr; void *g = nullptr; cudaStream_t s = nullptr; int64_t gen = -1; } fock_key_;
+    int fock_seen_ = 0;                  // consecutive eager builds with fock_key_
+    double fock_stats_[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // what one captured build adds to the handle's counters
+    int64_t store_gen_ = 0;              // bumped whenever the lists / values are rebuilt or released
+    int fock_enqueue(int nmat, const double *dDJ, const double *dDK, double *dG, cudaStream_t s, double *stats);
+    void drop_fock_graph();
     int join(cudaStream_t s);
     unsigned int *d_counters_ = nullptr; // work-queue heads, one per ERI launch (rotating)
     int counter_next_ = 0;

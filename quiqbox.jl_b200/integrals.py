@@ -57,7 +57,7 @@ class DeviceBasis:
     def stats(self, reset=False):
         out = np.zeros(16)
         _l.check(_l.load().qbx_stats(self.handle, _l.ptr(out), int(reset)))
-        keys = ["launches", "eri_seconds", "digest_seconds", "prim_quartets", "model_flops", "digest_bytes"]
+        keys = ["launches", "eri_seconds", "digest_seconds", "prim_quartets", "model_flops", "digest_bytes", "fock_graph_launches"]
         return dict(zip(keys, out.tolist()))
 
 

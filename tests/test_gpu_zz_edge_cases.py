@@ -183,3 +183,37 @@ def test_tight_contracted_shells_keep_their_digits(backend):
     i2 = _unique_quartets(d2.nbf)
     R2 = oracle.eri_list_quad(oracle.OracleBasis(d2.data), i2)
     assert np.max(np.abs(qb.elecRepulsions(d2)[tuple(i2.T)] - R2)) < 1e-12 * np.max(np.abs(R2))      # was 2e-7 with the transfer
+
+
+@pytest.mark.gpu
+def test_repeated_fock_builds_replay_a_graph_and_stay_correct():
+    """The stored-mode Fock build is captured into a CUDA graph the second time a handle sees the same device buffers
+    (csrc/engine.cu: Engine::fock) and replayed afterwards.  Five builds on one handle -- eager, captured, three
+    replays -- with different densities must each match the oracle; a new store on the same handle (other screening
+    threshold) must drop the graph (its lists are gone) and still be right; UHF-shaped builds (two exchange densities)
+    take their own capture."""
+    from molecules import h2o
+    nuc, xyz = h2o()
+    bs = sum((qb.genGaussTypeOrbSeq(c, s, "cc-pVDZ") for s, c in zip(nuc, xyz)), [])
+    db = qb.DeviceBasis(bs)
+    n = len(bs)
+    Tref = oracle.OracleBasis(qb.MultiOrbitalData.from_orbitals(bs)).eri_tensor(canonical=True)
+    eri = qb.DeviceERI(db, mode="stored", screen_tol=0.0)
+    for k in range(5):
+        DJ, DK = rand_sym(n, 10 + k), rand_sym(n, 20 + k)
+        G = eri.getGcore(DJ, [DK])[0]
+        assert np.max(np.abs(G - oracle.getGcore(Tref, DJ, DK))) < 1e-10, k
+    for k in range(3):                                       # nmat = 2 on the same handle: another key, another capture
+        DJ, DKa, DKb = rand_sym(n, 30 + k), rand_sym(n, 40 + k), rand_sym(n, 50 + k)
+        Ga, Gb = eri.getGcore(DJ, [DKa, DKb])
+        assert np.max(np.abs(Ga - oracle.getGcore(Tref, DJ, DKa))) < 1e-10
+        assert np.max(np.abs(Gb - oracle.getGcore(Tref, DJ, DKb))) < 1e-10
+    eri2 = qb.DeviceERI(db, mode="stored", screen_tol=1e-13)  # re-stores on the same basis handle: lists rebuilt
+    for k in range(3):
+        DJ, DK = rand_sym(n, 60 + k), rand_sym(n, 70 + k)
+        G = eri2.getGcore(DJ, [DK])[0]
+        assert np.max(np.abs(G - oracle.getGcore(Tref, DJ, DK))) < 1e-9
+    st = db.stats()
+    assert st["launches"] > 11 * 20                           # replays are counted like the launches they stand for
+    assert st["fock_graph_launches"] == 4 + 2 + 2             # builds 2..5, 2..3 and 2..3 of the three series
+    db.close()

@@ -275,6 +275,16 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+// stream capture / graphs: not emulated -- capture always fails and the library runs the eager path
+typedef struct cuemuGraph *cudaGraph_t;
+typedef struct cuemuGraphExec *cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorInvalidValue; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorInvalidValue; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t, unsigned long long = 0) { *e = nullptr; return cudaErrorInvalidValue; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorInvalidValue; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 struct cudaFuncAttributes { size_t localSizeBytes, sharedSizeBytes; int numRegs, maxThreadsPerBlock; };
 template <class K> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, K) { memset(a, 0, sizeof(*a)); if (getenv("QBX_EMU_FAKE_SPILL")) a->localSizeBytes = 1024; return cudaSuccess; }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
