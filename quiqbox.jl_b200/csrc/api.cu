@@ -386,6 +386,25 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
+    if (b->staged_nmat < nmat) {
+        qbx_pool_free(b->d_DJ); qbx_pool_free(b->d_DK); qbx_pool_free(b->d_G);
+        b->d_DJ = b->d_DK = b->d_G = nullptr; b->staged_nmat = 0;      // (an early return below must not leave dangling pointers)
+        QBX_CUDA(qbx_dmalloc(&b->d_DJ, n2));
+        QBX_CUDA(qbx_dmalloc(&b->d_DK, n2 * 2));
+        QBX_CUDA(qbx_dmalloc(&b->d_G, n2 * 2));
+        b->staged_nmat = 2;
+    }
+    // The caller's matrices are pageable: they go through the library's pinned staging area (one memcpy each, then a DMA
+    // that runs while the host checks the symmetry), and G comes back the same way -- a pageable cudaMemcpyAsync of
+    // these 1.3 MB matrices costs 0.2-0.3 ms each and blocks the host.
+    std::lock_guard<std::mutex> stage_lock(qbx_staging_mutex());
+    char *stage = (char *)qbx_staging(n2 * (1 + 2 * (size_t)nmat));
+    if (!stage) { qbx_set_error("qbx_fock_build: pinned staging allocation failed"); return QBX_ERR_NOMEM; }
+    double *hDJ = (double *)stage, *hDK = (double *)(stage + n2), *hG = (double *)(stage + n2 * (1 + (size_t)nmat));
+    memcpy(hDJ, DJ, n2);
+    QBX_CUDA(cudaMemcpyAsync(b->d_DJ, hDJ, n2, cudaMemcpyHostToDevice, g_stream));
+    memcpy(hDK, DK, n2 * nmat);
+    QBX_CUDA(cudaMemcpyAsync(b->d_DK, hDK, n2 * nmat, cudaMemcpyHostToDevice, g_stream));
     if (b->mode == 0 || b->mode == 1) {
         // the packed-store digestion is only valid for symmetric densities (include/qbx.h); reject anything else here
         // instead of returning a mode-dependent result
@@ -401,25 +420,17 @@ extern "C" int qbx_fock_build(qbx_basis *b, int nmat, const double *DJ, const do
                             ok &= fabs(v - w) <= 1e-10 * std::max(1.0, std::max(fabs(v), fabs(w)));   // (false for NaN)
                         }
             if (!ok) {
+                cudaStreamSynchronize(g_stream);                 // the staging area is in flight
                 qbx_set_error("qbx_fock_build: DJ and DK must be symmetric matrices (stored and direct modes)");
                 return QBX_ERR_ARG;
             }
         }
     }
-    if (b->staged_nmat < nmat) {
-        qbx_pool_free(b->d_DJ); qbx_pool_free(b->d_DK); qbx_pool_free(b->d_G);
-        b->d_DJ = b->d_DK = b->d_G = nullptr; b->staged_nmat = 0;      // (an early return below must not leave dangling pointers)
-        QBX_CUDA(qbx_dmalloc(&b->d_DJ, n2));
-        QBX_CUDA(qbx_dmalloc(&b->d_DK, n2 * 2));
-        QBX_CUDA(qbx_dmalloc(&b->d_G, n2 * 2));
-        b->staged_nmat = 2;
-    }
-    QBX_CUDA(cudaMemcpyAsync(b->d_DJ, DJ, n2, cudaMemcpyHostToDevice, g_stream));
-    QBX_CUDA(cudaMemcpyAsync(b->d_DK, DK, n2 * nmat, cudaMemcpyHostToDevice, g_stream));
     rc = qbx_fock_device(b, nmat, b->d_DJ, b->d_DK, b->d_G, g_stream);
-    if (rc) return rc;
-    QBX_CUDA(cudaMemcpyAsync(G, b->d_G, n2 * nmat, cudaMemcpyDeviceToHost, g_stream));
+    if (rc) { cudaStreamSynchronize(g_stream); return rc; }
+    QBX_CUDA(cudaMemcpyAsync(hG, b->d_G, n2 * nmat, cudaMemcpyDeviceToHost, g_stream));
     QBX_CUDA(cudaStreamSynchronize(g_stream));
+    memcpy(G, hG, n2 * nmat);
     return QBX_OK;
 }
 
