@@ -301,8 +301,22 @@ struct EriClass {
 // 1 to 6561 primitive quartets, so a static grid-stride assignment leaves most of the GPU idle
 // behind the few threads that drew a heavy task (it halved the throughput at 1/8 of the list,
 // i.e. on 8 GPUs); with the queue the light chunks at the end fill the tail.
+// resident blocks the register allocation aims at, by total angular momentum (A/B builds: tools/gpu_ab_eri.sh)
+// (B200, (H2O)16, profiles/r02/ab_eri_launch_bounds.log: L = 3 classes at 2 blocks of 256 threads = 128 registers:
+// (pp|ps) 2.80 -> 2.50 ms, (ds|ps) 2.19 -> 1.75 ms; at 3 blocks 4.56 / 2.71 ms; L = 4 classes at 2 blocks: (pp|pp) 0.59 -> 1.50 ms.)
+#ifndef QBX_ERI_MINB_L2
+#define QBX_ERI_MINB_L2 3
+#endif
+#ifndef QBX_ERI_MINB_L3
+#define QBX_ERI_MINB_L3 2
+#endif
+#ifndef QBX_ERI_MINB_L4
+#define QBX_ERI_MINB_L4 1
+#endif
+__host__ __device__ constexpr int eri_min_blocks(int L) { return L <= 2 ? QBX_ERI_MINB_L2 : (L == 3 ? QBX_ERI_MINB_L3 : (L == 4 ? QBX_ERI_MINB_L4 : 1)); }
+
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(QBX_ERI_THREADS, (LA + LB + LC + LD <= 2 ? 3 : 1)) eri_class_kernel(ClassArgs p)
+__global__ void __launch_bounds__(QBX_ERI_THREADS, eri_min_blocks(LA + LB + LC + LD)) eri_class_kernel(ClassArgs p)
 {
     using EC = EriClass<LA, LB, LC, LD>;
     extern __shared__ double boys_smem[];

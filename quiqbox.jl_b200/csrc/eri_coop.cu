@@ -264,6 +264,11 @@ __device__ __forceinline__ void boys_rt(const BoysTable &tb, const double *inv_o
 #ifndef COOP_WARPS
 #define COOP_WARPS 4
 #endif
+#ifndef QBX_COOP_MINB
+#define QBX_COOP_MINB 3                 // resident blocks of 128 threads the register allocation aims at: 168 registers.  A/B on a B200
+                                        // (tools/gpu_ab_coop.sh, profiles/r02/ab_coop_launch_bounds.log): five d-rich classes 2.92 ms unbounded,
+                                        // 2.41 ms at 3 blocks, 2.47 ms at 4 (128 registers, more spills)
+#endif
 #ifndef COOP_BATCH
 #define COOP_BATCH 4
 #endif
@@ -439,7 +444,7 @@ struct Coop2 {
 };
 
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(COOP_WARPS * 32) eri_coop2_kernel(CoopArgs p)
+__global__ void __launch_bounds__(COOP_WARPS * 32, QBX_COOP_MINB) eri_coop2_kernel(CoopArgs p)
 {
     using C2 = Coop2<LA, LB, LC, LD>;
     extern __shared__ double smem[];
