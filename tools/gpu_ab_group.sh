@@ -13,10 +13,14 @@ import json, sys
 name, out = sys.argv[1], sys.argv[2]
 d = json.loads([l for l in open(f"{out}/bench_{name}.json") if l.startswith("{")][-1])
 pc = {c["class"]: c for c in d["per_class"]}
-print("%-14s (00|00) %.3f ms %.1f TF   (10|00) %.3f ms %.1f TF   eri %.2f ms  step %.2f  regs: %s" % (name, pc["(00|00)"]["ms"], pc["(00|00)"]["tflops_model"],
-      pc["(10|00)"]["ms"], pc["(10|00)"]["tflops_model"], d["eri_ms"], d["ms_per_step"], open(f"{out}/res_{name}.txt").read()))
+print("%-14s (00|00) %.3f ms %.1f TF   (10|00) %.3f ms %.1f TF   (20|00) %.3f ms  eri %.2f ms  step %.2f  regs: %s" % (name, pc["(00|00)"]["ms"], pc["(00|00)"]["tflops_model"],
+      pc["(10|00)"]["ms"], pc["(10|00)"]["tflops_model"], pc["(20|00)"]["ms"], d["eri_ms"], d["ms_per_step"], open(f"{out}/res_{name}.txt").read()))
 PY
 }
+if [ $# -gt 0 ]; then
+  for v in "$@"; do run "${v%%:*}" ${v#*:}; done
+  exit 0
+fi
 run base
 run p_minb1 -DQBX_GRP_MINB_P=1
 run p_192x2 -DQBX_GRP_THREADS_P=192
