@@ -1191,7 +1191,10 @@ int Engine::fock_enqueue(int nmat, const double *dDJ, const double *dDK, double 
             if (mode_ == 0) {
                 a.tasks = tl.tasks; a.ntasks = tl.n; a.vals = vals_[bc][kc];
                 cudaStream_t ds = side_[kside++ % kSide];
-                int rc = ops->digest(a, ds);
+                // group classes with an s or p bra: one lane per group task (eri_group.cu); QBX_DIGEST_GROUP=0: per quartet
+                static const bool by_group = !(getenv("QBX_DIGEST_GROUP") && atoi(getenv("QBX_DIGEST_GROUP")) == 0);
+                int rc = (by_group && tl.ngt > 0) ? qbx_group_digest(ops->la, groups_, a, tl, ds) : -1;
+                if (rc == -1) rc = ops->digest(a, ds);
                 if (rc) return rc;
                 stats[0] += 1;
                 stats[5] += (double)tl.n * ops->ncomp * sizeof(double);

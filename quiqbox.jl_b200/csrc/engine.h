@@ -87,6 +87,7 @@ void qbx_scan_counts(const int *cnt, int n, int64_t *off, int64_t *d_total, cuda
 struct GroupSet {
     int ng = 0;
     int *nmem = nullptr, *members = nullptr, *prim_off = nullptr;
+    int *flip = nullptr;                 // bit m: member m lists its shells as (shell of Q, shell of P) -- the pair list orders by shell index
     double *soa = nullptr;
     int2 *soa_idx = nullptr;
     std::vector<int> h_nprim, h_nmem;
@@ -102,6 +103,7 @@ int qbx_group_fill(const GroupSet &G, const struct DevPairSet &B, const struct D
                    int nranks, TaskScratch &ts, const int64_t *h_total, TaskList &tl, double *d_stat, int *d_nheavy,
                    cudaStream_t s);
 int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList &tl, cudaStream_t s);
+int qbx_group_digest(int la, const GroupSet &G, const DigestArgs &a, const TaskList &tl, cudaStream_t s);   // -1: not served
 
 class Engine {
 public:

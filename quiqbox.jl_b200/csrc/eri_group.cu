@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "digest.cuh"
 
 #define QBX_GRP_MAXMEM 9
 #define QBX_GRP_NF (5 + QBX_GRP_MAXMEM)      // eta, Qx, Qy, Qz, Kgeom, cc[9]
@@ -348,6 +349,161 @@ __global__ void k_group_fill(GroupTables T, int ng, double pref, const int *orde
         }
 }
 
+
+// ------------------------------------------------------------------ J/K digestion of the group classes: lane = group task
+// The slot list of an (x s|ss) class is laid out group task by group task: up to 9 member quartets (3 shells C of one
+// centre x 3 shells D of another) behind ONE bra pair.  The per-quartet kernel of digest.cuh sees them as 32 unrelated
+// lanes whose C repeats in runs of 3 and whose D repeats with stride 3: segmented sums three lanes long, REDs of one
+// instruction hitting the same address three times, and a quarter of the slots empty (screened members) -- the (ps|ss)
+// launch was the longest of the whole Fock build.  Here ONE LANE digests a whole group task: the <= 3 distinct C and the
+// <= 3 distinct D of its members are found on the fly, K[x,c] and K[x,d] (x = the bra functions a.., b) are summed over the
+// members in registers and leave as one RED per distinct shell, the density elements D[x,c], D[x,d] are loaded once per
+// distinct shell, empty slots cost one compare.  J[ab] is summed over the lanes that share the bra pair as before.
+template <int LA>
+__global__ void __launch_bounds__(128, LA == 0 ? 5 : 3) digest_group_kernel(DigestArgs p, const int *__restrict__ gt_bra,
+                                                                          const int *__restrict__ gt_grp, const int *__restrict__ gt_off,
+                                                                          const int *__restrict__ grp_nmem, const int *__restrict__ grp_flip, int ngt)
+{
+    constexpr int NA = NC(LA), NX = NA + 1;
+    const unsigned nblk = (unsigned)((ngt + 127) / 128);
+    const unsigned R = nblk < (unsigned)p.spread ? nblk : (unsigned)p.spread, Cb = (nblk + R - 1) / R;
+    const unsigned blk = (blockIdx.x % R) * Cb + blockIdx.x / R;          // blocks resident together sit on different bra rows
+    if (blk >= nblk) return;
+    const int t0 = (int)(blk * 128 + threadIdx.x), lane = threadIdx.x & 31;
+    if (t0 - lane >= ngt) return;
+    const bool live = t0 < ngt;
+    const int t = live ? t0 : ngt - 1;
+    const int ib = __ldg(gt_bra + t), off = __ldg(gt_off + t);
+    const int grp = __ldg(gt_grp + t);
+    const int nmem = live ? __ldg(grp_nmem + grp) : 0;
+    const int flip = __ldg(grp_flip + grp);                     // members listed as (shell of Q, shell of P): swapped below, so
+                                                                // that "c" is always one of P's <= 3 shells and "d" one of Q's
+    const int4 rb = __ldg(p.bra_info + ib);
+    const int N = p.nbf, ia = rb.z, ibf = rb.w;
+    const double fab = rb.x == rb.y ? 0.5 : 1.0;
+    const int64_t nt = p.ntasks;
+    bool headAB;
+    int endAB;
+    seg_runs(ib, 0, lane, headAB, endAB);
+    for (int mm = 0; mm < p.nmat; ++mm) {
+        const double *__restrict__ DKm = p.DK + (int64_t)mm * N * N;
+        double *Ktm = p.Kt + (int64_t)mm * N * N;
+        const bool coul = mm == 0;
+        int cfun[3] = {-1, -1, -1}, dfun[3] = {-1, -1, -1};
+        double dxc[NX][3], dxd[NX][3], kxc[NX][3], kxd[NX][3], jab[NA], dab[NA];
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { dxc[x][k] = dxd[x][k] = 0.0; kxc[x][k] = kxd[x][k] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < NA; ++a) { jab[a] = 0.0; dab[a] = coul ? __ldg(p.DJ + ibf + (int64_t)N * (ia + a)) : 0.0; }
+#pragma unroll
+        for (int m = 0; m < QBX_GRP_MAXMEM; ++m) {
+            if (m >= nmem) break;
+            const int64_t slot = (int64_t)off + m;
+            const int j = __ldg(&p.tasks[slot].y);
+            if (j < 0) continue;                                           // member screened out / not unique
+            const int4 rk = __ldg(p.ket_info + j);
+            const bool sw = (flip >> m) & 1;
+            const int ic = sw ? rk.w : rk.z, id = sw ? rk.z : rk.w;       // (ab|cd) = (ab|dc): every update below is symmetric in it
+            double f = fab;
+            if (rk.x == rk.y) f *= 0.5;
+            if (p.same_class && j == ib) f *= 0.5;
+            // position of C and D among the distinct shells seen so far; a new one brings its density elements along
+            bool pc[3], pd[3];
+            {
+                const bool h0 = cfun[0] == ic, h1 = cfun[1] == ic, h2 = cfun[2] == ic;
+                const bool fresh = !(h0 || h1 || h2);
+                pc[0] = h0 || (fresh && cfun[0] < 0);
+                pc[1] = h1 || (fresh && cfun[0] >= 0 && cfun[1] < 0);
+                pc[2] = h2 || (fresh && cfun[0] >= 0 && cfun[1] >= 0);
+                if (fresh) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (pc[k]) {
+                            cfun[k] = ic;
+#pragma unroll
+                            for (int x = 0; x < NX; ++x) dxc[x][k] = __ldg(DKm + ic + (int64_t)N * (x < NA ? ia + x : ibf));
+                        }
+                }
+            }
+            {
+                const bool h0 = dfun[0] == id, h1 = dfun[1] == id, h2 = dfun[2] == id;
+                const bool fresh = !(h0 || h1 || h2);
+                pd[0] = h0 || (fresh && dfun[0] < 0);
+                pd[1] = h1 || (fresh && dfun[0] >= 0 && dfun[1] < 0);
+                pd[2] = h2 || (fresh && dfun[0] >= 0 && dfun[1] >= 0);
+                if (fresh) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (pd[k]) {
+                            dfun[k] = id;
+#pragma unroll
+                            for (int x = 0; x < NX; ++x) dxd[x][k] = __ldg(DKm + id + (int64_t)N * (x < NA ? ia + x : ibf));
+                        }
+                }
+            }
+            double dsc[NX], dsd[NX];                                       // D[x,c], D[x,d] of this member
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                dsc[x] = pc[0] ? dxc[x][0] : (pc[1] ? dxc[x][1] : dxc[x][2]);
+                dsd[x] = pd[0] ? dxd[x][0] : (pd[1] ? dxd[x][1] : dxd[x][2]);
+            }
+            const double dcd = coul ? __ldg(p.DJ + id + (int64_t)N * ic) : 0.0;
+            double jcd = 0.0, kbc = 0.0, kbd = 0.0;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const double x = f * __ldg(p.vals + (int64_t)a * nt + slot);
+                jab[a] = fma(dcd, x, jab[a]);
+                jcd = fma(dab[a], x, jcd);
+                const double kac = dsd[NA] * x, kad = dsc[NA] * x;         // K[a,c] += D[b,d] v   K[a,d] += D[b,c] v
+                kbc = fma(dsd[a], x, kbc);                                 // K[b,c] += D[a,d] v
+                kbd = fma(dsc[a], x, kbd);                                 // K[b,d] += D[a,c] v
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (pc[k]) kxc[a][k] += kac;
+                    if (pd[k]) kxd[a][k] += kad;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (pc[k]) kxc[NA][k] += kbc;
+                if (pd[k]) kxd[NA][k] += kbd;
+            }
+            if (coul) atomicAdd(p.Jt + id + (int64_t)N * ic, 2.0 * jcd);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (cfun[k] >= 0) {
+#pragma unroll
+                for (int x = 0; x < NX; ++x)
+                    if (kxc[x][k] != 0.0) atomicAdd(Ktm + cfun[k] + (int64_t)N * (x < NA ? ia + x : ibf), kxc[x][k]);
+            }
+            if (dfun[k] >= 0) {
+#pragma unroll
+                for (int x = 0; x < NX; ++x)
+                    if (kxd[x][k] != 0.0) atomicAdd(Ktm + dfun[k] + (int64_t)N * (x < NA ? ia + x : ibf), kxd[x][k]);
+            }
+        }
+        if (coul) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const double js = seg_sum(2.0 * jab[a], endAB, lane);
+                if (headAB && js != 0.0) atomicAdd(p.Jt + ibf + (int64_t)N * (ia + a), js);
+            }
+        }
+    }
+}
+
+template <int LA>
+int launch_digest_group(const DigestArgs &a, const TaskList &tl, const GroupSet &G, cudaStream_t s)
+{
+    const unsigned nblk = (unsigned)((tl.ngt + 127) / 128);
+    const unsigned R = nblk < (unsigned)a.spread ? nblk : (unsigned)a.spread, Cb = (nblk + R - 1) / R;
+    digest_group_kernel<LA><<<R * Cb, 128, 0, s>>>(a, tl.gt_bra, tl.gt_grp, tl.gt_off, G.nmem, G.flip, tl.ngt);
+    QBX_CUDA(cudaGetLastError());
+    return QBX_OK;
+}
 }  // namespace
 
 // ------------------------------------------------------------------ host side
@@ -452,12 +608,16 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         }
         out.ng = (int)ng0;
         out.h_nprim.resize(ng0); out.h_nmem.resize(ng0);
-        std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0);
+        std::vector<int> mem(ng0 * QBX_GRP_MAXMEM, -1), poff(ng0 + 1, 0), flip(ng0, 0);
         for (size_t n = 0; n < ng0; ++n) {
             const int g = order[n];
             out.h_nprim[n] = cnt[g];
             out.h_nmem[n] = nmem[g];
-            for (int m = 0; m < nmem[g]; ++m) mem[n * QBX_GRP_MAXMEM + m] = members[(size_t)g * QBX_GRP_MAXMEM + m];
+            for (int m = 0; m < nmem[g]; ++m) {
+                const int j = members[(size_t)g * QBX_GRP_MAXMEM + m];
+                mem[n * QBX_GRP_MAXMEM + m] = j;
+                if (pg_of[ss_pairs[j].x] != gp_pq[g].first) flip[n] |= 1 << m;
+            }
             poff[n + 1] = poff[n] + cnt[g];
         }
         std::vector<int2> soa_idx(ng0);
@@ -473,11 +633,13 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
         const size_t n_soa = (size_t)QBX_GRP_NF * poff.back();
         QBX_CUDA(qbx_dmalloc(&out.nmem, ng0 * sizeof(int)));
         QBX_CUDA(qbx_dmalloc(&out.members, mem.size() * sizeof(int)));
+        QBX_CUDA(qbx_dmalloc(&out.flip, ng0 * sizeof(int)));
         QBX_CUDA(qbx_dmalloc(&out.prim_off, poff.size() * sizeof(int)));
         QBX_CUDA(qbx_dmalloc(&out.soa, std::max<size_t>(1, n_soa) * sizeof(double)));
         QBX_CUDA(qbx_dmalloc(&out.soa_idx, ng0 * sizeof(int2)));
         QBX_CUDA(cudaMemcpyAsync(out.nmem, out.h_nmem.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice, st));
         QBX_CUDA(cudaMemcpyAsync(out.members, mem.data(), mem.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        QBX_CUDA(cudaMemcpyAsync(out.flip, flip.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice, st));
         QBX_CUDA(cudaMemcpyAsync(out.soa_idx, soa_idx.data(), ng0 * sizeof(int2), cudaMemcpyHostToDevice, st));
         QBX_CUDA(cudaMemcpyAsync(out.prim_off, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         QBX_CUDA(cudaMemcpyAsync(d_order, order.data(), ng0 * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -495,7 +657,7 @@ int qbx_group_build(const std::vector<HostShell> &sh, const std::vector<int2> &s
 
 void qbx_group_free(GroupSet &g)
 {
-    qbx_pool_free(g.nmem); qbx_pool_free(g.members); qbx_pool_free(g.prim_off); qbx_pool_free(g.soa); qbx_pool_free(g.soa_idx);
+    qbx_pool_free(g.nmem); qbx_pool_free(g.members); qbx_pool_free(g.flip); qbx_pool_free(g.prim_off); qbx_pool_free(g.soa); qbx_pool_free(g.soa_idx);
     g = GroupSet();
 }
 
@@ -554,4 +716,15 @@ int qbx_group_eri(int la, const GroupSet &G, const ClassArgs &a, const TaskList 
     }
     qbx_set_error("internal: no group kernel for this class");
     return QBX_ERR_STATE;
+}
+
+// J/K digestion of a stored group class with one lane per group task; -1 = not served (the per-quartet kernel does it).
+int qbx_group_digest(int la, const GroupSet &G, const DigestArgs &a, const TaskList &tl, cudaStream_t s)
+{
+    if (tl.ngt <= 0) return QBX_OK;
+    switch (la) {
+    case 0: return launch_digest_group<0>(a, tl, G, s);
+    case 1: return launch_digest_group<1>(a, tl, G, s);
+    }
+    return -1;                                               // (ds|ss): 7 x 6 accumulators per lane do not fit
 }

@@ -167,10 +167,11 @@ assert db.info()["n_quartets"] == 13652        # Schwarz bounds do not depend on
 '''
 
 
-@pytest.mark.parametrize("env", [{}, {"QBX_EMU_LANE_ORDER": "reverse"}, {"QBX_DIGEST_SPREAD": "1"},
+@pytest.mark.parametrize("env", [{}, {"QBX_EMU_LANE_ORDER": "reverse"}, {"QBX_DIGEST_SPREAD": "1"}, {"QBX_DIGEST_SPREAD": "3"},
+                                 {"QBX_DIGEST_GROUP": "0"},
                                  {"QBX_GC": "0"}, {"QBX_EMU_SMS": "148"},
                                  {"QBX_GC": "0", "QBX_EMU_LANE_ORDER": "reverse", "QBX_EMU_SMS": "148"}],
-                         ids=["default", "reverse-lane-order", "task-order-blocks", "no-general-contraction",
+                         ids=["default", "reverse-lane-order", "task-order-blocks", "3-block-slots-ragged-grid", "per-quartet-group-digest", "no-general-contraction",
                               "148-SMs-short-lists", "no-general-contraction-reverse-148"])
 def test_fock_build_switches_vs_oracle(env):
     """(H2O)2/6-31G with Schwarz screening (ragged rows: most warps straddle several (bra pair, C)
