@@ -9,7 +9,7 @@ if [ "${1:-}" = "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
       python bench.py --steps 2 --warmup 1 --no-e2e --cpu-seconds 0 > "$OUT/ncu_launches.log" 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      --kernel-name regex:"digest_kernel|eri_group_kernel|eri_coop2|eri_class_kernel" --launch-skip 42 --launch-count 42 \
+      --kernel-name regex:"digest_kernel|digest_group_kernel|eri_group_kernel|eri_coop2|eri_class_kernel" --launch-skip 42 --launch-count 42 \
       -o /tmp/full python tools/e2e_probe.py 2 > "$OUT/ncu_full.log" 2>&1
   ncu -i /tmp/full.ncu-rep --page raw --csv > "$OUT/ncu_raw.csv" 2>/dev/null
   python tools/ncu_summary.py "$OUT/ncu_raw.csv" > "$OUT/ncu_summary.md" 2>&1
