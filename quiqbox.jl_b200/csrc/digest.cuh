@@ -29,7 +29,9 @@
 // shared-memory CAS-adds, and a run table with per-run butterflies -- and every one of them lost against this one
 // (17.5 / 22 / 25 / 46 ms against 11-12 ms for the (H2O)16 build).  The numbers, the ncu counters and the reason --
 // the list's runs of equal shell C are 5-11 quartets long, not tens, because the pair lists are sorted by
-// primitive count for the ERI kernels -- are in profiles/r02/digest_history.md.
+// primitive count for the ERI kernels -- are in profiles/r02/digest_history.md.  What did win in round 2: the value slab
+// and kept-row sizes below by A/B (12.2 -> 11.4 ms), and a kernel of its own for the general-contraction classes
+// (ss|ss), (ps|ss), one lane per group task (eri_group.cu: digest_group_kernel; 11.3 -> 10.9 ms).
 #pragma once
 #include "engine.h"
 
