@@ -350,6 +350,12 @@ __global__ void k_group_fill(GroupTables T, int ng, double pref, const int *orde
 }
 
 
+#ifndef QBX_DGRP_MINB_S
+#define QBX_DGRP_MINB_S 5               // resident blocks of 128 threads the register allocation aims at (A/B: tools/gpu_ab_digest.sh)
+#endif
+#ifndef QBX_DGRP_MINB_P
+#define QBX_DGRP_MINB_P 3
+#endif
 // ------------------------------------------------------------------ J/K digestion of the group classes: lane = group task
 // The slot list of an (x s|ss) class is laid out group task by group task: up to 9 member quartets (3 shells C of one
 // centre x 3 shells D of another) behind ONE bra pair.  The per-quartet kernel of digest.cuh sees them as 32 unrelated
@@ -360,7 +366,7 @@ __global__ void k_group_fill(GroupTables T, int ng, double pref, const int *orde
 // members in registers and leave as one RED per distinct shell, the density elements D[x,c], D[x,d] are loaded once per
 // distinct shell, empty slots cost one compare.  J[ab] is summed over the lanes that share the bra pair as before.
 template <int LA>
-__global__ void __launch_bounds__(128, LA == 0 ? 5 : 3) digest_group_kernel(DigestArgs p, const int *__restrict__ gt_bra,
+__global__ void __launch_bounds__(128, LA == 0 ? QBX_DGRP_MINB_S : QBX_DGRP_MINB_P) digest_group_kernel(DigestArgs p, const int *__restrict__ gt_bra,
                                                                           const int *__restrict__ gt_grp, const int *__restrict__ gt_off,
                                                                           const int *__restrict__ grp_nmem, const int *__restrict__ grp_flip, int ngt)
 {

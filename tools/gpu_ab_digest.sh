@@ -5,7 +5,7 @@ set -u
 OUT=gpurun_out/ab_digest; mkdir -p "$OUT"
 run() {  # name defs...
   local name=$1; shift
-  touch quiqbox.jl_b200/csrc/digest.cuh
+  touch quiqbox.jl_b200/csrc/digest.cuh quiqbox.jl_b200/csrc/eri_group.cu
   QBX_NVCC_DEFS="$*" python quiqbox.jl_b200/build.py -j 32 > "$OUT/build_$name.log" 2>&1 || { echo "build $name failed"; tail -3 "$OUT/build_$name.log"; return; }
   python bench.py --steps 8 --warmup 3 --no-e2e --cpu-seconds 0 > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
   python - "$name" "$OUT" "$*" <<'PY'
