@@ -193,9 +193,10 @@ extern "C" int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, do
     int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
-    int64_t *d_idx = nullptr; double *d_out = nullptr;
-    QBX_CUDA(qbx_dmalloc(&d_idx, 4 * n * sizeof(int64_t)));
-    QBX_CUDA(qbx_dmalloc(&d_out, n * sizeof(double)));
+    QbxScratch<int64_t> d_idx;                               // (freed on every return path)
+    QbxScratch<double> d_out;
+    QBX_CUDA(d_idx.alloc(4 * n * sizeof(int64_t)));
+    QBX_CUDA(d_out.alloc(n * sizeof(double)));
     QBX_CUDA(cudaMemcpyAsync(d_idx, ijkl, 4 * n * sizeof(int64_t), cudaMemcpyHostToDevice, g_stream));
     rc = qbx_launch_generic_quartets(b->flat, n, d_idx, d_out, g_stream);
     if (!rc) {
@@ -203,7 +204,6 @@ extern "C" int qbx_eri_quartets(qbx_basis *b, int64_t n, const int64_t *ijkl, do
         QBX_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    qbx_pool_free(d_idx); qbx_pool_free(d_out);
     if (!rc)
         for (int64_t t = 0; t < n; ++t)
             if (out[t] != out[t]) { qbx_set_error("qbx_eri_quartets: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
@@ -218,15 +218,14 @@ extern "C" int qbx_eri_tensor(qbx_basis *b, double *out, int64_t out_bytes)
     int rc = qbx_ensure_init();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
-    double *d_t = nullptr;
-    QBX_CUDA(qbx_dmalloc(&d_t, need));
+    QbxScratch<double> d_t;
+    QBX_CUDA(d_t.alloc(need));
     if (b->eng) rc = b->eng->fill_tensor(d_t, g_stream, b->stats);
     else { rc = qbx_launch_generic_tensor(b->flat, d_t, g_stream); b->stats[0] += 1; }
     if (!rc) {
         QBX_CUDA(cudaMemcpyAsync(out, d_t, need, cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    qbx_pool_free(d_t);
     if (!rc && !b->eng)
         for (int64_t t = 0; t < N * N * N * N; ++t)
             if (out[t] != out[t]) { qbx_set_error("qbx_eri_tensor: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
@@ -444,11 +443,11 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(b->mu);
     const size_t n2 = (size_t)b->nbf * b->nbf * sizeof(double);
-    double *dZ = nullptr, *dR = nullptr, *dO = nullptr;
-    QBX_CUDA(qbx_dmalloc(&dO, n2));
+    QbxScratch<double> dZ, dR, dO;                           // (freed on every return path)
+    QBX_CUDA(dO.alloc(n2));
     if (kind == 2 && nnuc > 0) {
-        QBX_CUDA(qbx_dmalloc(&dZ, nnuc * sizeof(double)));
-        QBX_CUDA(qbx_dmalloc(&dR, 3 * nnuc * sizeof(double)));
+        QBX_CUDA(dZ.alloc(nnuc * sizeof(double)));
+        QBX_CUDA(dR.alloc(3 * nnuc * sizeof(double)));
         QBX_CUDA(cudaMemcpyAsync(dZ, Z, nnuc * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         QBX_CUDA(cudaMemcpyAsync(dR, R, 3 * nnuc * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     }
@@ -458,7 +457,6 @@ extern "C" int qbx_one_body(qbx_basis *b, int kind, int64_t nnuc, const double *
         QBX_CUDA(cudaMemcpyAsync(out, dO, n2, cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    qbx_pool_free(dZ); qbx_pool_free(dR); qbx_pool_free(dO);
     if (!rc)
         for (int64_t t = 0; t < b->nbf * b->nbf; ++t)
             if (out[t] != out[t]) { qbx_set_error("qbx_one_body: angular momentum beyond the generic kernel's range"); return QBX_ERR_RANGE; }
@@ -476,16 +474,15 @@ extern "C" int qbx_boys(int64_t n, const double *T, int mmax, int table, double 
         if (!(T[i] >= 0.0)) { qbx_set_error("qbx_boys: T must be >= 0"); return QBX_ERR_ARG; }
     int rc = qbx_ensure_init();
     if (rc) return rc;
-    double *dT = nullptr, *dO = nullptr;
-    QBX_CUDA(qbx_dmalloc(&dT, n * sizeof(double)));
-    QBX_CUDA(qbx_dmalloc(&dO, n * (mmax + 1) * sizeof(double)));
+    QbxScratch<double> dT, dO;
+    QBX_CUDA(dT.alloc(n * sizeof(double)));
+    QBX_CUDA(dO.alloc(n * (mmax + 1) * sizeof(double)));
     QBX_CUDA(cudaMemcpyAsync(dT, T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     rc = qbx_launch_boys(n, dT, mmax, table, dO, g_stream);
     if (!rc) {
         QBX_CUDA(cudaMemcpyAsync(out, dO, n * (mmax + 1) * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
         QBX_CUDA(cudaStreamSynchronize(g_stream));
     }
-    qbx_pool_free(dT); qbx_pool_free(dO);
     return rc;
 }
 

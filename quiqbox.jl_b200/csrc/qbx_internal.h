@@ -52,6 +52,18 @@ struct QbxPoolDeferScope {
     QbxPoolDeferScope(const QbxPoolDeferScope &) = delete;
     QbxPoolDeferScope &operator=(const QbxPoolDeferScope &) = delete;
 };
+// Scratch block of an entry point: returned to the pool when the holder goes out of scope, also on the early returns of
+// QBX_CUDA (the blocking free: the work that uses the block has finished when the pool gets it back).
+template <class T>
+struct QbxScratch {
+    T *p = nullptr;
+    QbxScratch() = default;
+    ~QbxScratch() { if (p) qbx_pool_free(p); }
+    QbxScratch(const QbxScratch &) = delete;
+    QbxScratch &operator=(const QbxScratch &) = delete;
+    cudaError_t alloc(size_t bytes) { return qbx_pool_malloc((void **)&p, bytes); }
+    operator T *() const { return p; }
+};
 void *qbx_pinned(size_t bytes);
 void *qbx_staging(size_t bytes);
 std::mutex &qbx_staging_mutex();
