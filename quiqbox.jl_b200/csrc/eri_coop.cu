@@ -264,6 +264,9 @@ __device__ __forceinline__ void boys_rt(const BoysTable &tb, const double *inv_o
 #ifndef COOP_WARPS
 #define COOP_WARPS 4
 #endif
+#ifndef QBX_COOP_ONE_PASS
+#define QBX_COOP_ONE_PASS 1
+#endif
 #ifndef QBX_COOP_MINB
 #define QBX_COOP_MINB 3                 // resident blocks of 128 threads the register allocation aims at: 168 registers.  A/B on a B200
                                         // (tools/gpu_ab_coop.sh, profiles/r02/ab_coop_launch_bounds.log): five d-rich classes 2.92 ms unbounded,
@@ -360,13 +363,17 @@ struct Coop2 {
     static constexpr int ASTR = NACC | 1, XSTR = NKET | 1;
     static constexpr int acc2_off = VT, x2_off = VT + NKET * ASTR;
     static constexpr int BUF = (WT > x2_off + NAB * XSTR ? WT : x2_off + NAB * XSTR);
-    // passes: q < NPH owns g = GB + 32 q + lane; the last pass (only if GB > 0) owns g = lane < GB
+    // passes: q < NPH owns g = GB + 32 q + lane; the last pass (only if GB > 0) owns g = lane < GB.
+    // ONE_PASS: when all GT stacked components fit one warp ((dp|dp): 20) the low degrees go to the lanes behind the
+    // contracted ones, g = GB + lane for lane < GT - GB and g = lane - (GT - GB) up to lane GT - 1: every recurrence
+    // entry is then one instruction stream instead of two with 16 and 4 active lanes (QBX_COOP_ONE_PASS=0: two passes).
+    static constexpr bool ONE_PASS = QBX_COOP_ONE_PASS && GT <= 32 && GB > 0;
     static constexpr int NPH = (GT - GB + 31) / 32;
-    static constexpr int NP = NPH + (GB > 0 ? 1 : 0);
+    static constexpr int NP = ONE_PASS ? 1 : NPH + (GB > 0 ? 1 : 0);
     static __host__ __device__ constexpr int pass_lo(int q) { return q < NPH ? GB + 32 * q : 0; }
     static __host__ __device__ constexpr int pass_hi(int q) { return q < NPH ? (GB + 32 * q + 32 < GT ? GB + 32 * q + 32 : GT) : GB; }
     // does pass q hold targets of transfer level f?  (decided at compile time: whole passes drop out of a level)
-    static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return pass_lo(q) < ghi(f) && pass_hi(q) > glo(f); }
+    static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return ONE_PASS || (pass_lo(q) < ghi(f) && pass_hi(q) > glo(f)); }
 
     struct LaneInfo {            // per pass
         int g;                   // own stacked index (or -1: lane idle in this pass)
@@ -379,8 +386,8 @@ struct Coop2 {
 
     static __device__ __forceinline__ void lane_info(int q, int lane, double *B, LaneInfo &I)
     {
-        const int g = pass_lo(q) + lane;
-        I.g = g < pass_hi(q) ? g : -1;
+        const int g = ONE_PASS ? (lane < GT - GB ? GB + lane : lane - (GT - GB)) : pass_lo(q) + lane;
+        I.g = ONE_PASS ? (lane < GT ? g : -1) : (g < pass_hi(q) ? g : -1);
         int e = 0;
         while (e < L && S1(e + 1) <= g) ++e;
         const int c = g - S1(e);
