@@ -341,7 +341,7 @@ struct Coop2 {
     static constexpr int NA = NC(LA), NB = NC(LB), NCc = NC(LC), ND = NC(LD), NAB = NA * NB;
     static constexpr int NACC = NCSUM(LA, E), NKET = NCSUM(LC, F);
     static constexpr int GT = S1(E + 1);                       // stacked bra components that take part: degrees 0..E
-    static constexpr int GB = S1(LA);                          // lane 0 of pass 0 owns the first contracted component
+    static constexpr int GB = S1(LA);                          // first contracted stacked component
     static_assert(F >= 1 && NACC <= 32 && NKET <= 32, "Coop2: class outside the layout's assumptions");
     // ket level f keeps degrees e in [elo(f), E] = global stacked range [glo(f), ghi(f)), at orders m = 0..F-f
     static __host__ __device__ constexpr int elo(int f) { return (LA - (F - f)) > 0 ? (LA - (F - f)) : 0; }
@@ -363,17 +363,22 @@ struct Coop2 {
     static constexpr int ASTR = NACC | 1, XSTR = NKET | 1;
     static constexpr int acc2_off = VT, x2_off = VT + NKET * ASTR;
     static constexpr int BUF = (WT > x2_off + NAB * XSTR ? WT : x2_off + NAB * XSTR);
-    // passes: q < NPH owns g = GB + 32 q + lane; the last pass (only if GB > 0) owns g = lane < GB.
-    // ONE_PASS: when all GT stacked components fit one warp ((dp|dp): 20) the low degrees go to the lanes behind the
-    // contracted ones, g = GB + lane for lane < GT - GB and g = lane - (GT - GB) up to lane GT - 1: every recurrence
-    // entry is then one instruction stream instead of two with 16 and 4 active lanes (QBX_COOP_ONE_PASS=0: two passes).
-    static constexpr bool ONE_PASS = QBX_COOP_ONE_PASS && GT <= 32 && GB > 0;
-    static constexpr int NPH = (GT - GB + 31) / 32;
-    static constexpr int NP = ONE_PASS ? 1 : NPH + (GB > 0 ? 1 : 0);
-    static __host__ __device__ constexpr int pass_lo(int q) { return q < NPH ? GB + 32 * q : 0; }
-    static __host__ __device__ constexpr int pass_hi(int q) { return q < NPH ? (GB + 32 * q + 32 < GT ? GB + 32 * q + 32 : GT) : GB; }
+    // Lane layout: the GT stacked bra components are cut into passes of 32 lanes FROM THE TOP: the high passes
+    // q < NPH own g = P0 + 32 q + lane, a last, short pass owns the P0 = GT mod 32 lowest components (none if GT is
+    // a multiple of 32).  (dp|dp): GT = 20 -> one pass, every recurrence entry is one instruction stream with 20 lanes
+    // (it used to be 16 + 4 lanes in two: 1.21 -> 0.94 ms on the B200).  (dd|..): GT = 35 -> 32 + 3 lanes, and the short
+    // pass only holds degrees 0 and 1, which the upper ket levels do not need: it drops out of them at compile time
+    // (the earlier split at the first contracted component, 25 + 10 lanes, kept both passes in every level; measured:
+    // the same 0.52 / 0.40 / 0.23 ms for (dd|pp), (dd|ds), (dd|dp) either way -- profiles/r02/ab_coop_launch_bounds.log).
+    // The contracted components g >= GB accumulate in the lane that owns them (always pass 0: GT - GB <= 32).
+    static constexpr int P0 = QBX_COOP_ONE_PASS ? (GT > 32 ? GT % 32 : 0) : GB;     // QBX_COOP_ONE_PASS=0: the old layout, split at GB
+    static constexpr int NPH = (GT - P0 + 31) / 32;
+    static constexpr int NP = NPH + (P0 > 0 ? 1 : 0);
+    static_assert(NPH == 1, "Coop2: the contracted components must sit in pass 0");
+    static __host__ __device__ constexpr int pass_lo(int q) { return q < NPH ? P0 + 32 * q : 0; }
+    static __host__ __device__ constexpr int pass_hi(int q) { return q < NPH ? (P0 + 32 * q + 32 < GT ? P0 + 32 * q + 32 : GT) : P0; }
     // does pass q hold targets of transfer level f?  (decided at compile time: whole passes drop out of a level)
-    static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return ONE_PASS || (pass_lo(q) < ghi(f) && pass_hi(q) > glo(f)); }
+    static __host__ __device__ constexpr bool pass_in_level(int q, int f) { return pass_lo(q) < ghi(f) && pass_hi(q) > glo(f); }
 
     struct LaneInfo {            // per pass
         int g;                   // own stacked index (or -1: lane idle in this pass)
@@ -386,8 +391,8 @@ struct Coop2 {
 
     static __device__ __forceinline__ void lane_info(int q, int lane, double *B, LaneInfo &I)
     {
-        const int g = ONE_PASS ? (lane < GT - GB ? GB + lane : lane - (GT - GB)) : pass_lo(q) + lane;
-        I.g = ONE_PASS ? (lane < GT ? g : -1) : (g < pass_hi(q) ? g : -1);
+        const int g = pass_lo(q) + lane;
+        I.g = g < pass_hi(q) ? g : -1;
         int e = 0;
         while (e < L && S1(e + 1) <= g) ++e;
         const int c = g - S1(e);
@@ -439,7 +444,7 @@ struct Coop2 {
                                 if (nf > 0) v = fma(nf * i2e, fma(-rhoe, I[q].gp[t1], I[q].gp[t0]), v);
                                 v = fma(nh[q][ax], I[q].dn[ax][s1], v);
                                 I[q].gp[dst] = v;
-                                if (m == 0 && f1 >= LC && q == 0 && lane < NACC) acc[NCSUM(LC, f1 - 1) + cf] += v;
+                                if (m == 0 && f1 >= LC && q == 0 && g >= GB) acc[NCSUM(LC, f1 - 1) + cf] += v;
                             }
                         }
                     }
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, QBX_COOP_MINB) eri_coop2_kern
                     for (int x = 0; x < 3; ++x) nh[q][x] = I[q].n[x] * hinv;
                 }
                 if constexpr (LC == 0) {
-                    if (lane < C2::NACC) acc[0] += *I[0].v0;
+                    if (I[0].g >= C2::GB) acc[0] += *I[0].v0;
                 }
                 __syncwarp();
                 C2::template ket_vrr<0>(I, nh, QC, WQ, i2e, rhoe, acc, lane);
@@ -514,9 +519,9 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, QBX_COOP_MINB) eri_coop2_kern
         }
         // contracted [e0|f0] -> shared, one row per stacked ket component
         __syncwarp();
-        if (lane < C2::NACC) {
+        if (I[0].g >= C2::GB) {                                 // the lane that owns a contracted component holds its sums
 #pragma unroll
-            for (int kk = 0; kk < C2::NKET; ++kk) B[C2::acc2_off + kk * C2::ASTR + lane] = acc[kk];
+            for (int kk = 0; kk < C2::NKET; ++kk) B[C2::acc2_off + kk * C2::ASTR + (I[0].g - C2::GB)] = acc[kk];
         }
         __syncwarp();
         // bra horizontal recurrence: lane = stacked ket component
